@@ -1,0 +1,121 @@
+/* tfl.h -- C ABI of the B200-native TF-Locoformer separation forward path.
+ *
+ * The reference (chynggi/mss-tf-locoformer) is pure Python on PyTorch; the "FFI" a
+ * maintainer binds is therefore ctypes.  Every entry point below
+ * replaces a reference nn.Module.forward (file:line cited per function), takes plain
+ * device pointers + sizes + a cudaStream_t, is asynchronous on that stream, never
+ * allocates or frees device memory and keeps no pointer past the call (the packed-weight
+ * buffer and workspace are caller-owned).  Return value: 0 = OK, < 0 = error
+ * (tfl_last_error() gives the message for the calling thread).
+ *
+ * Activation layout: channels-last [B, Tf, F, C] fp32 ("x"); spectrograms are
+ * [B, (S,) Tf, F] interleaved (re, im) fp32 == torch.complex64.
+ */
+#ifndef TFL_H_
+#define TFL_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tfl_stream_t; /* == cudaStream_t */
+
+#define TFL_PRECISION_FP32 0 /* CUDA-core fp32 everywhere: the <=1e-4 / >=70 dB parity mode            */
+#define TFL_PRECISION_BF16 1 /* tcgen05 bf16 MMAs with fp32 TMEM accumulation, fp32 residual stream      */
+#define TFL_AXIS_FREQ 0      /* sequences run along F, one per (b, t)  -- freq_path                      */
+#define TFL_AXIS_TIME 1      /* sequences run along Tf, one per (b, f) -- frame_path                     */
+
+/* Constructor arguments of TFLocoformerMSS (models/mss_tflocoformer.py:104-129) /
+ * TFLocoformerSeparator (standalone/tflocoformer_separator.py:59-81). */
+typedef struct tfl_config {
+  int32_t n_fft;        /* 0 for spectrogram-in/spectrogram-out separators */
+  int32_t hop;
+  int32_t n_src;        /* n_sources / num_spk */
+  int32_t n_layers;
+  int32_t emb_dim;      /* C */
+  int32_t num_groups;   /* RMSGroupNorm groups */
+  int32_t tf_order;     /* 0 = "ft", 1 = "tf" */
+  int32_t n_heads;
+  int32_t attention_dim;
+  int32_t rope;         /* 1 = pos_enc "rope", 0 = "nope" */
+  int32_t macaron;      /* 1 when ffn_type is a 2-list */
+  int32_t ffn_hidden0;  /* hidden dim of ffn[0] (post-attention; LAST entry of the config list) */
+  int32_t ffn_hidden1;  /* hidden dim of ffn[1] (pre-attention; FIRST entry), 0 if !macaron    */
+  int32_t conv_kernel;  /* conv1d_kernel; conv1d_shift must be 1 */
+  int32_t enc_in_ch;    /* input channels of the encoder conv: 2 (re, im); 0 = no conv encoder/decoder (band-split) */
+  float eps;
+} tfl_config;
+
+typedef struct tfl_plan tfl_plan;
+
+int tfl_version(void);
+const char* tfl_last_error(void);
+/* Kernels launched by this library since it was loaded (host-side counter). */
+uint64_t tfl_launch_count(void);
+
+int tfl_plan_create(const tfl_config* cfg, tfl_plan** out);
+void tfl_plan_destroy(tfl_plan* plan);
+
+/* Number of fp32 weight pointers tfl_pack_weights expects, and the packed size.
+ * Pointer order == reference state_dict order:
+ *   conv.0.weight, conv.0.bias, conv.1.weight, conv.1.bias,                      (if enc_in_ch)
+ *   per layer i, per path p in (freq_path, frame_path):
+ *     [ffn_norm.0.gamma, ffn_norm.1.gamma if macaron], then per ffn j in (0[,1]):
+ *     conv1d.weight, conv1d.bias, deconv1d.weight, deconv1d.bias;
+ *     attn_norm.gamma, [attn.rope.freqs if rope], attn.qkv.weight, attn.aggregate_heads.0.weight
+ *   deconv.weight, deconv.bias                                                  (if enc_in_ch) */
+int tfl_num_weight_tensors(const tfl_plan* plan);
+size_t tfl_packed_bytes(const tfl_plan* plan);
+int tfl_pack_weights(const tfl_plan* plan, const float* const* weights, int n_weights,
+                     void* packed, size_t packed_bytes, tfl_stream_t stream);
+
+size_t tfl_workspace_bytes(const tfl_plan* plan, int batch, int n_frames, int n_freq, int precision);
+
+/* models/mss_tflocoformer.py:36-54 + :207-214.  audio [B, T] -> spec [B, Tf, F, 2]. */
+int tfl_stft(const tfl_plan* plan, const void* packed, const float* audio, int batch, int n_samples,
+             float* spec, tfl_stream_t stream);
+/* :141-146, :218-219.  spec [B, Tf, F, Cin] -> x [B, Tf, F, C] (conv 3x3 + gLN). */
+int tfl_enc_conv_gln(const tfl_plan* plan, const void* packed, const float* spec, int batch, int n_frames,
+                     int n_freq, float* x, void* workspace, size_t ws_bytes, tfl_stream_t stream);
+/* :682-706.  x [rows, C] -> y [rows, C] with the gamma of (layer, axis, which) where
+ * which = 0: ffn_norm.0, 1: ffn_norm.1, 2: attn_norm. */
+int tfl_rms_group_norm(const tfl_plan* plan, const void* packed, int layer, int axis, int which,
+                       const float* x, float* y, int64_t rows, tfl_stream_t stream);
+/* :443-447 / :459-462 -> :626-655.  In place: x += ConvSwiGLU(RMSGroupNorm(x)) along `axis`. */
+int tfl_conv_swiglu_ffn(const tfl_plan* plan, const void* packed, int layer, int axis, int ffn_index,
+                        float* x, int batch, int n_frames, int n_freq, void* workspace, size_t ws_bytes,
+                        int precision, tfl_stream_t stream);
+/* :452-456 -> :504-559.  In place: x += MHSA_RoPE(RMSGroupNorm(x)) along `axis`. */
+int tfl_rope_attn(const tfl_plan* plan, const void* packed, int layer, int axis, float* x, int batch,
+                  int n_frames, int n_freq, void* workspace, size_t ws_bytes, int precision,
+                  tfl_stream_t stream);
+/* :182, :229-237.  x [B, Tf, F, C] -> est [B, S, Tf, F, 2] (complex64 [B, S, Tf, F]). */
+int tfl_dec_conv(const tfl_plan* plan, const void* packed, const float* x, int batch, int n_frames,
+                 int n_freq, float* est, tfl_stream_t stream);
+/* :56-75, :239-250.  est [B, S, Tf, F, 2] -> audio [S, B, n_samples] (all sources, one launch). */
+int tfl_istft_ola(const tfl_plan* plan, const void* packed, const float* est, int batch, int n_frames,
+                  int n_samples, float* audio, tfl_stream_t stream);
+/* :222-226.  All n_layers TFLocoformerBlocks in place on x. */
+int tfl_blocks(const tfl_plan* plan, const void* packed, float* x, int batch, int n_frames, int n_freq,
+               void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream);
+/* TFLocoformerMSS.forward, :184-258.  mixture [B, T] -> audio [S, B, T]; est_spec (optional,
+ * may be NULL) receives the separated spectrograms [B, S, Tf, F, 2]. */
+int tfl_forward(const tfl_plan* plan, const void* packed, const float* mixture, int batch, int n_samples,
+                float* audio, float* est_spec, void* workspace, size_t ws_bytes, int precision,
+                tfl_stream_t stream);
+/* TFLocoformerSeparator.forward, standalone/tflocoformer_separator.py:131-171.
+ * spec [B, T, F, 2] -> est [B, S, T, F, 2]. */
+int tfl_separator_forward(const tfl_plan* plan, const void* packed, const float* spec, int batch,
+                          int n_frames, int n_freq, float* est, void* workspace, size_t ws_bytes,
+                          int precision, tfl_stream_t stream);
+/* Full-track stitch (new): track[S, n_track] += window(seg) * seg_audio[S, B, seg_len]
+ * for segments seg_index0 .. seg_index0 + B - 1 of n_seg_total at 50 % overlap. */
+int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, int seg_index0,
+                    int n_seg_total, float* track, int64_t n_track, tfl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFL_H_ */

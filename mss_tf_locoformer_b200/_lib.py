@@ -1,0 +1,66 @@
+"""ctypes binding of include/tfl.h.  There is NO fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libtfl_b200.so")
+
+
+class TflConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_fft", "hop", "n_src", "n_layers", "emb_dim", "num_groups", "tf_order", "n_heads", "attention_dim",
+        "rope", "macaron", "ffn_hidden0", "ffn_hidden1", "conv_kernel", "enc_in_ch")] + [("eps", C.c_float)]
+
+
+class TflError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_P, _I, _Z, _L = C.c_void_p, C.c_int, C.c_size_t, C.c_int64
+SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include/tfl.h
+    "tfl_version": (_I, []),
+    "tfl_last_error": (C.c_char_p, []),
+    "tfl_launch_count": (C.c_uint64, []),
+    "tfl_plan_create": (_I, [C.POINTER(TflConfig), C.POINTER(_P)]),
+    "tfl_plan_destroy": (None, [_P]),
+    "tfl_num_weight_tensors": (_I, [_P]),
+    "tfl_packed_bytes": (_Z, [_P]),
+    "tfl_pack_weights": (_I, [_P, C.POINTER(_P), _I, _P, _Z, _P]),
+    "tfl_workspace_bytes": (_Z, [_P, _I, _I, _I, _I]),
+    "tfl_stft": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "tfl_enc_conv_gln": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    "tfl_rms_group_norm": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "tfl_conv_swiglu_ffn": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _Z, _I, _P]),
+    "tfl_rope_attn": (_I, [_P, _P, _I, _I, _P, _I, _I, _I, _P, _Z, _I, _P]),
+    "tfl_dec_conv": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "tfl_istft_ola": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "tfl_blocks": (_I, [_P, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
+    "tfl_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),
+    "tfl_separator_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _I, _P]),
+    "tfl_segment_ola": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
+}
+
+
+def load():
+    """Load libtfl_b200.so (built by ``python -m mss_tf_locoformer_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built. Run "
+            "`python -m mss_tf_locoformer_b200.build` (or __graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        raise TflError(load().tfl_last_error().decode(errors="replace") or f"tfl error {status}")

@@ -1,0 +1,98 @@
+// Shared declarations for the TF-Locoformer sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tfl.h"
+
+namespace tfl {
+
+void set_error(const char* fmt, ...);
+
+#define TFL_CHECK(cond, ...)                         \
+  do {                                               \
+    if (!(cond)) {                                   \
+      ::tfl::set_error(__VA_ARGS__);                 \
+      return -1;                                     \
+    }                                                \
+  } while (0)
+
+#define TFL_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::tfl::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+extern unsigned long long g_launches;  // kernels launched by this library since load (bench.py's gpu_launches)
+#define TFL_LAUNCH_CHECK()          \
+  do {                              \
+    ++::tfl::g_launches;            \
+    TFL_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// Maps (sequence s, position p) of one Locoformer path onto the channels-last residual
+// stream x[B, Tf, F, C] without materialising the reference's transposes
+// (models/mss_tflocoformer.py:339-344): element offset = (s / inner) * outer_stride
+// + (s % inner) * inner_stride + p * pos_stride.
+struct SeqMap {
+  int inner;
+  long long outer_stride, inner_stride, pos_stride;
+  __host__ __device__ __forceinline__ long long base(int s) const {
+    return (long long)(s / inner) * outer_stride + (long long)(s % inner) * inner_stride;
+  }
+};
+
+inline SeqMap make_seq_map(int axis, int n_frames, int n_freq, int C) {
+  SeqMap m;
+  if (axis == TFL_AXIS_FREQ) {  // s = b*Tf + t, p = f
+    m.inner = 1 << 30; m.outer_stride = 0; m.inner_stride = (long long)n_freq * C; m.pos_stride = C;
+  } else {                      // s = b*F + f, p = t
+    m.inner = n_freq; m.outer_stride = (long long)n_frames * n_freq * C; m.inner_stride = C;
+    m.pos_stride = (long long)n_freq * C;
+  }
+  return m;
+}
+
+inline SeqMap make_dense_map(long long seq_stride, long long pos_stride) {
+  SeqMap m; m.inner = 1 << 30; m.outer_stride = 0; m.inner_stride = seq_stride; m.pos_stride = pos_stride;
+  return m;
+}
+
+// ---- packed weight image -------------------------------------------------------------
+struct FfnPack {
+  size_t gamma;      // [C] fp32
+  size_t w1;         // fp32 [K][C][2H] with (value, gate) column-interleaved
+  size_t b1;         // [2H] interleaved
+  size_t w2;         // fp32 [K][H][C], tap order reversed (tap k' multiplies g[i + k'])
+  size_t b2;         // [C]
+  size_t tc;         // bf16 tcgen05 image (0 = none)
+  int hidden;
+};
+struct PathPack {
+  FfnPack ffn[2];
+  size_t attn_gamma, wqkv /*[C][3A]*/, wo /*[A][C]*/, rope /*[hd/2]*/;
+  size_t tc_qkv, tc_wo;
+};
+struct PackLayout {
+  size_t enc_w /*[3][3][Cin][C]*/, enc_b, gln_w, gln_b, dec_w /*[3][3][C][2S] flipped*/, dec_b;
+  size_t twiddle /*[n_fft/2] float2*/, window /*[n_fft]*/;
+  std::vector<PathPack> paths;  // [2*layer + axis]
+  size_t total;
+};
+
+}  // namespace tfl
+
+struct tfl_plan {
+  tfl_config cfg;
+  tfl::PackLayout lay;
+  int head_dim;
+  int n_ffn;
+  int sm_count;
+};

@@ -1,0 +1,554 @@
+// fp32 CUDA-core kernels: the bandwidth-bound stages (STFT, encoder conv + gLN,
+// RMSGroupNorm, decoder, iSTFT + OLA, segment stitch) used in BOTH precision modes, plus
+// the fp32 tap-GEMM / attention kernels that make up TFL_PRECISION_FP32 (the <= 1e-4
+// parity mode).  References are to /root/reference/models/mss_tflocoformer.py.
+#pragma once
+#include "common.cuh"
+
+namespace tfl {
+
+// ======================================================================================
+// Shared-memory radix-2 FFT (decimation in time on bit-reversed input).
+// tw[k] = exp(-2 pi i k / N), k < N/2.  All threads of the CTA participate.
+// ======================================================================================
+template <bool INVERSE>
+__device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int n, int log_n) {
+  for (int s = 1; s <= log_n; ++s) {
+    const int half = 1 << (s - 1);
+    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+      const int j = i & (half - 1);
+      const int a = ((i >> (s - 1)) << s) + j;
+      const int b = a + half;
+      float2 w = __ldg(&tw[j << (log_n - s)]);
+      if (INVERSE) w.y = -w.y;
+      const float2 u = buf[a], v = buf[b];
+      const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
+      buf[a] = make_float2(u.x + tr, u.y + ti);
+      buf[b] = make_float2(u.x - tr, u.y - ti);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int bitrev(int i, int log_n) { return (int)(__brev((unsigned)i) >> (32 - log_n)); }
+
+// --------------------------------------------------------------------------------------
+// K1 stft: reflect pad + periodic Hann + FFT, one CTA per frame; writes channels-last
+// (re, im) so the reference's stack + transpose (:207-214) never exist.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ audio, int n_samples, int n_fft,
+                                                   int log_n, int hop, int n_frames,
+                                                   const float2* __restrict__ tw, const float* __restrict__ win,
+                                                   float* __restrict__ spec) {
+  extern __shared__ float2 fbuf[];
+  const int t = blockIdx.x, b = blockIdx.y;
+  const float* a = audio + (size_t)b * n_samples;
+  const int pad = n_fft >> 1;
+  for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
+    int n = t * hop + i - pad;
+    if (n < 0) n = -n;
+    if (n >= n_samples) n = 2 * (n_samples - 1) - n;
+    fbuf[bitrev(i, log_n)] = make_float2(__ldg(&a[n]) * __ldg(&win[i]), 0.f);
+  }
+  __syncthreads();
+  fft_smem<false>(fbuf, tw, n_fft, log_n);
+  const int n_freq = pad + 1;
+  float2* out = reinterpret_cast<float2*>(spec) + ((size_t)b * n_frames + t) * n_freq;
+  for (int k = threadIdx.x; k < n_freq; k += blockDim.x) out[k] = fbuf[k];
+}
+
+// --------------------------------------------------------------------------------------
+// K7 istft_ola: one CTA per (hop block, source, batch).  For each frame overlapping the
+// block: Hermitian-extend, inverse FFT in smem, window, accumulate; then divide by the
+// sum of squared windows and store (:56-75).  Output audio[src][b][n].
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ est, int n_src, int n_frames,
+                                                        int n_fft, int log_n, int hop, int n_samples,
+                                                        const float2* __restrict__ tw,
+                                                        const float* __restrict__ win, float* __restrict__ audio,
+                                                        int batch) {
+  extern __shared__ float2 fbuf[];
+  float* acc = reinterpret_cast<float*>(fbuf + n_fft);
+  float* env = acc + hop;
+  const int m = blockIdx.x, src = blockIdx.y, b = blockIdx.z;
+  const int pad = n_fft >> 1, n_freq = pad + 1;
+  const int q_lo = m * hop + pad;  // padded-signal coordinate of the block's first sample
+  for (int i = threadIdx.x; i < hop; i += blockDim.x) { acc[i] = 0.f; env[i] = 0.f; }
+  int t_min = (q_lo - n_fft) / hop + 1;
+  if (q_lo - n_fft < 0) t_min = 0;
+  int t_max = (q_lo + hop - 1) / hop;
+  if (t_max > n_frames - 1) t_max = n_frames - 1;
+  const float inv_n = 1.f / (float)n_fft;
+  for (int t = t_min; t <= t_max; ++t) {
+    const float2* x = reinterpret_cast<const float2*>(est) + (((size_t)b * n_src + src) * n_frames + t) * n_freq;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_freq; k += blockDim.x) {
+      float2 v = __ldg(&x[k]);
+      if (k == 0 || k == pad) {
+        v.y = 0.f;  // irfft ignores the imaginary part of DC and Nyquist
+        fbuf[bitrev(k, log_n)] = v;
+      } else {
+        fbuf[bitrev(k, log_n)] = v;
+        fbuf[bitrev(n_fft - k, log_n)] = make_float2(v.x, -v.y);
+      }
+    }
+    __syncthreads();
+    fft_smem<true>(fbuf, tw, n_fft, log_n);
+    for (int i = threadIdx.x; i < hop; i += blockDim.x) {
+      const int off = q_lo + i - t * hop;
+      if (off >= 0 && off < n_fft) {
+        const float w = __ldg(&win[off]);
+        acc[i] += fbuf[off].x * inv_n * w;
+        env[i] += w * w;
+      }
+    }
+  }
+  float* out = audio + ((size_t)src * batch + b) * n_samples;
+  for (int i = threadIdx.x; i < hop; i += blockDim.x) {
+    const int n = m * hop + i;
+    if (n < n_samples) out[n] = acc[i] / env[i];
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// K2 encoder: Conv2d(Cin, C, 3x3, pad 1) direct + per-sample sum / sum-of-squares
+// partials (double) for the global layer norm (:141-146).  One thread per (position, 4
+// channels); deterministic two-level reduction.
+// --------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256) enc_conv_kernel(const float* __restrict__ spec, int n_frames, int n_freq,
+                                                       int C, const float* __restrict__ w /*[3][3][CIN][C]*/,
+                                                       const float* __restrict__ bias, float* __restrict__ y,
+                                                       double* __restrict__ partial /*[B][gridDim.x][2]*/) {
+  extern __shared__ float wsm[];  // 9*CIN*C + C
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 9 * CIN * C; i += blockDim.x) wsm[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) wsm[9 * CIN * C + i] = bias[i];
+  __syncthreads();
+  const int c4n = C >> 2;
+  const long long per_sample = (long long)n_frames * n_freq * c4n;
+  const float* in = spec + (size_t)b * n_frames * n_freq * CIN;
+  float* out = y + (size_t)b * n_frames * n_freq * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < per_sample;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) << 2;
+    const long long pos = idx / c4n;
+    const int f = (int)(pos % n_freq), t = (int)(pos / n_freq);
+    float4 a = *reinterpret_cast<const float4*>(&wsm[9 * CIN * C + c]);
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt) {
+      const int tt = t + dt - 1;
+      if (tt < 0 || tt >= n_frames) continue;
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        const int ff = f + df - 1;
+        if (ff < 0 || ff >= n_freq) continue;
+        const float* px = in + ((size_t)tt * n_freq + ff) * CIN;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float xv = __ldg(&px[ci]);
+          const float4 wv = *reinterpret_cast<const float4*>(&wsm[((dt * 3 + df) * CIN + ci) * C + c]);
+          a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y);
+          a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(&out[pos * C + c]) = a;
+    s1 += (double)a.x + (double)a.y + (double)a.z + (double)a.w;
+    s2 += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
+  }
+  __shared__ double r1[256], r2[256];
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = r1[0];
+    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r2[0];
+  }
+}
+
+__global__ void gln_finalize_kernel(const double* __restrict__ partial, int n_part, double count, float eps,
+                                    float* __restrict__ stats /*[B][2] mean, rstd*/) {
+  const int b = blockIdx.x;
+  __shared__ double r1[256], r2[256];
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+    s1 += partial[((size_t)b * n_part + i) * 2];
+    s2 += partial[((size_t)b * n_part + i) * 2 + 1];
+  }
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = r1[0] / count;
+    double var = r2[0] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[b * 2] = (float)mean;
+    stats[b * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+__global__ void __launch_bounds__(256) gln_apply_kernel(float* __restrict__ x, long long per_sample4, int C,
+                                                        const float* __restrict__ stats,
+                                                        const float* __restrict__ gw, const float* __restrict__ gb) {
+  const int b = blockIdx.y;
+  const float mean = stats[b * 2], rstd = stats[b * 2 + 1];
+  float4* p = reinterpret_cast<float4*>(x) + (size_t)b * per_sample4;
+  const int c4n = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    float4 v = p[i];
+    const float4 w = *reinterpret_cast<const float4*>(&gw[c]);
+    const float4 bb = *reinterpret_cast<const float4*>(&gb[c]);
+    v.x = (v.x - mean) * rstd * w.x + bb.x; v.y = (v.y - mean) * rstd * w.y + bb.y;
+    v.z = (v.z - mean) * rstd * w.z + bb.z; v.w = (v.w - mean) * rstd * w.w + bb.w;
+    p[i] = v;
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// K3 rms_group_norm (:682-706): y = x / (||x_g|| * D^-1/2 + eps) * gamma.
+// A sub-warp of W lanes owns one (row, group); each lane holds one 128-bit chunk.
+// --------------------------------------------------------------------------------------
+template <int W, typename OutT>
+__global__ void __launch_bounds__(256) rms_group_norm_kernel(const float* __restrict__ x, OutT* __restrict__ y,
+                                                             long long rows, int C, int G,
+                                                             const float* __restrict__ gamma, float eps) {
+  const int D = C / G, lanes = D >> 2;
+  const float scale = rsqrtf((float)D);
+  const int sub = threadIdx.x % W;
+  const long long pairs = rows * G;
+  const long long stride = (long long)gridDim.x * (blockDim.x / W);
+  for (long long pr = (long long)blockIdx.x * (blockDim.x / W) + threadIdx.x / W;
+       pr < ((pairs + stride - 1) / stride) * stride; pr += stride) {
+    const bool active = pr < pairs && sub < lanes;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long off = 0;
+    int c = 0;
+    if (active) {
+      const long long row = pr / G;
+      c = (int)(pr % G) * D + (sub << 2);
+      off = row * C + c;
+      v = *reinterpret_cast<const float4*>(&x[off]);
+    }
+    float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o = W >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o, W);
+    if (active) {
+      const float denom = sqrtf(ss) * scale + eps;
+      const float4 g = *reinterpret_cast<const float4*>(&gamma[c]);
+      const float o0 = v.x / denom * g.x, o1 = v.y / denom * g.y, o2 = v.z / denom * g.z, o3 = v.w / denom * g.w;
+      if constexpr (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(&y[off]) = make_float4(o0, o1, o2, o3);
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(&y[off]) = pk;
+      }
+    }
+  }
+}
+
+// ======================================================================================
+// fp32 tap-GEMM:  out[r, n] = bias[n] + sum_{tap, c} A[s, j + tap - padL, c] * W[tap][c][n]
+// with flat row r = s * Sout + j and A rows outside [0, Sin) read as zero -- the exact
+// zero padding the reference applies AFTER the norm (:640-644).  One kernel serves the
+// conv1d (+SwiGLU epilogue), the transposed conv (+bias, +residual), the qkv projection
+// (+RoPE epilogue) and the head-merge projection (+residual).
+// ======================================================================================
+struct TapGemm {
+  const float* A; SeqMap amap; int Sin, Sout, padL, taps, Kc;
+  const float* W; const float* bias; int N; long long M;
+};
+
+constexpr int GBM = 128, GBN = 128, GBK = 8;
+
+struct EpiSwiGLU {  // columns are (value, gate) interleaved; writes hid[r][n/2]  (:648-649)
+  float* hid; int H;
+  __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float g = v[2 * i + 1]; o[i] = v[2 * i] * (g / (1.f + expf(-g))); }
+    float* dst = hid + r * H + (n0 >> 1);
+    if (n0 + 8 <= N) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    else for (int i = 0; i < 4; ++i) if (n0 + 2 * i < N) dst[i] = o[i];
+  }
+};
+
+struct EpiResidual {  // x[s, j, n] += v   (:447, :456, :462)
+  float* x; SeqMap omap;
+  __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
+    float* dst = x + omap.base(s) + (long long)j * omap.pos_stride + n0;
+    if (n0 + 8 <= N) {
+      float4 a = *reinterpret_cast<float4*>(dst), b = *reinterpret_cast<float4*>(dst + 4);
+      a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+      b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
+      *reinterpret_cast<float4*>(dst) = a; *reinterpret_cast<float4*>(dst + 4) = b;
+    } else for (int i = 0; i < 8; ++i) if (n0 + i < N) dst[i] += v[i];
+  }
+};
+
+struct EpiQkvRope {  // n -> (which, head, d); RoPE on q,k (interleaved pairs); out[which][s][head][j][d]
+  float* qkv; int A, hd, heads, L, nseq; const float* freqs;  // freqs == nullptr -> "nope"
+  __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const int n = n0 + i;
+      if (n >= N) break;
+      const int which = n / A, rem = n - which * A, head = rem / hd, d = rem - head * hd;
+      float a = v[i], b = v[i + 1];
+      if (freqs != nullptr && which < 2) {
+        const float ang = (float)j * __ldg(&freqs[d >> 1]);
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        const float ra = a * cs - b * sn, rb = b * cs + a * sn;
+        a = ra; b = rb;
+      }
+      float* dst = qkv + ((((size_t)which * nseq + s) * heads + head) * L + j) * hd + d;
+      *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+    }
+  }
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(256) tap_gemm_kernel(TapGemm p, Epi epi) {
+  __shared__ float As[2][GBK][GBM + 4];
+  __shared__ float Bs[2][GBK][GBN];
+  __shared__ long long row_base[GBM];
+  __shared__ int row_j[GBM], row_s[GBM];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * GBM;
+  const int n0 = blockIdx.y * GBN;
+  if (tid < GBM) {
+    const long long r = m0 + tid;
+    if (r < p.M) {
+      const int s = (int)(r / p.Sout), j = (int)(r - (long long)s * p.Sout);
+      row_s[tid] = s; row_j[tid] = j; row_base[tid] = p.amap.base(s);
+    } else { row_s[tid] = -1; row_j[tid] = 0; row_base[tid] = 0; }
+  }
+  __syncthreads();
+  const int a_row = tid >> 1, a_kq = (tid & 1) << 2;
+  const int b_row = tid >> 5, b_col = (tid & 31) << 2;
+  const int kt_per_tap = p.Kc / GBK, n_kt = p.taps * kt_per_tap;
+  const int my_s = row_s[a_row], my_j = row_j[a_row];
+  const long long my_base = row_base[a_row];
+
+  auto load_a = [&](int kt) -> float4 {
+    const int tap = kt / kt_per_tap, c0 = (kt - tap * kt_per_tap) * GBK;
+    const int pos = my_j + tap - p.padL;
+    if (my_s < 0 || pos < 0 || pos >= p.Sin) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(p.A + my_base + (long long)pos * p.amap.pos_stride + c0 + a_kq));
+  };
+  auto load_b = [&](int kt) -> float4 {
+    const int n = n0 + b_col;
+    if (n >= p.N) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(p.W + ((size_t)kt * GBK + b_row) * p.N + n));
+  };
+  auto stash = [&](int buf, float4 a, float4 b) {
+    As[buf][a_kq + 0][a_row] = a.x; As[buf][a_kq + 1][a_row] = a.y;
+    As[buf][a_kq + 2][a_row] = a.z; As[buf][a_kq + 3][a_row] = a.w;
+    *reinterpret_cast<float4*>(&Bs[buf][b_row][b_col]) = b;
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  stash(0, load_a(0), load_b(0));
+  __syncthreads();
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int cur = kt & 1;
+    float4 na, nb;
+    const bool more = kt + 1 < n_kt;
+    if (more) { na = load_a(kt + 1); nb = load_b(kt + 1); }
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) stash(cur ^ 1, na, nb);
+    __syncthreads();
+  }
+  const int nb0 = n0 + tx * 8;
+  if (nb0 >= p.N) return;
+  float bias[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bias[j] = (p.bias != nullptr && nb0 + j < p.N) ? __ldg(&p.bias[nb0 + j]) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = ty * 8 + i;
+    const int s = row_s[rl];
+    if (s < 0) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[i][j] + bias[j];
+    epi(s, row_j[rl], m0 + rl, nb0, p.N, v);
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// fp32 attention (:523-531): softmax(q k^T / sqrt(hd)) v, online softmax, one thread per
+// query, K/V tiles broadcast from shared memory.  q,k,v: [nseq][heads][L][hd].
+// --------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                       const float* __restrict__ v, float* __restrict__ o,
+                                                       int L, int hd, int heads, float scale) {
+  constexpr int TK = 64, CH = 16;
+  __shared__ float ks[TK][HD], vs[TK][HD];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  float qr[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) { qr[d] = (i < L && d < hd) ? q[base + (size_t)i * hd + d] * scale : 0.f; acc[d] = 0.f; }
+  float mx = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < L; j0 += TK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TK * HD; e += blockDim.x) {
+      const int jj = e / HD, d = e - jj * HD;
+      const bool ok = (j0 + jj < L) && (d < hd);
+      ks[jj][d] = ok ? k[base + (size_t)(j0 + jj) * hd + d] : 0.f;
+      vs[jj][d] = ok ? v[base + (size_t)(j0 + jj) * hd + d] : 0.f;
+    }
+    __syncthreads();
+    const int lim = min(TK, L - j0);
+    for (int c0 = 0; c0 < lim; c0 += CH) {
+      float sc[CH];
+      float cm = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) dot = fmaf(qr[d], ks[c0 + c][d], dot);
+        sc[c] = (c0 + c < lim) ? dot : -INFINITY;
+        cm = fmaxf(cm, sc[c]);
+      }
+      const float nm = fmaxf(mx, cm);
+      const float corr = expf(mx - nm);
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float pv = expf(sc[c] - nm);
+        l += pv;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = fmaf(pv, vs[c0 + c][d], acc[d]);
+      }
+      mx = nm;
+    }
+  }
+  if (i < L) {
+    const float inv = 1.f / l;
+    float* dst = o + ((size_t)s * L + i) * ((size_t)heads * hd) + (size_t)head * hd;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) if (d < hd) dst[d] = acc[d] * inv;
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// K6 decoder: ConvTranspose2d(C, 2S, 3x3, pad 1) as a 9-tap gather (:182); one warp per
+// position, lanes over channels, shuffle reduction; writes est[b][src][t][f][re/im].
+// wd layout: [9 taps][C][8] (tap = dt*3+df multiplies x[t+1-dt, f+1-df]).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_conv_kernel(const float* __restrict__ x, int n_frames, int n_freq, int C,
+                                                       int n_out, const float* __restrict__ wd,
+                                                       const float* __restrict__ bias, float* __restrict__ est,
+                                                       long long n_pos) {
+  extern __shared__ float wsm[];  // 9*C*8
+  for (int i = threadIdx.x; i < 9 * C * 8; i += blockDim.x) wsm[i] = wd[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n_src = n_out >> 1;
+  for (long long pos = (long long)blockIdx.x * wpb + warp; pos < n_pos; pos += (long long)gridDim.x * wpb) {
+    const int f = (int)(pos % n_freq);
+    const long long bt = pos / n_freq;
+    const int t = (int)(bt % n_frames), b = (int)(bt / n_frames);
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt) {
+      const int tt = t + 1 - dt;
+      if (tt < 0 || tt >= n_frames) continue;
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        const int ff = f + 1 - df;
+        if (ff < 0 || ff >= n_freq) continue;
+        const float* px = x + (((size_t)b * n_frames + tt) * n_freq + ff) * C;
+        const float* pw = wsm + (dt * 3 + df) * C * 8;
+        for (int c = lane << 2; c < C; c += 128) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(px + c));
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const float4 w0 = *reinterpret_cast<const float4*>(pw + (c + ci) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(pw + (c + ci) * 8 + 4);
+            acc[0] = fmaf(xs[ci], w0.x, acc[0]); acc[1] = fmaf(xs[ci], w0.y, acc[1]);
+            acc[2] = fmaf(xs[ci], w0.z, acc[2]); acc[3] = fmaf(xs[ci], w0.w, acc[3]);
+            acc[4] = fmaf(xs[ci], w1.x, acc[4]); acc[5] = fmaf(xs[ci], w1.y, acc[5]);
+            acc[6] = fmaf(xs[ci], w1.z, acc[6]); acc[7] = fmaf(xs[ci], w1.w, acc[7]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sh);
+    if (lane < n_out) {
+      float val = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) if (o == lane) val = acc[o];
+      val += __ldg(&bias[lane]);
+      const int src = lane >> 1, ri = lane & 1;
+      est[(((((size_t)b * n_src + src) * n_frames + t) * n_freq + f) << 1) + ri] = val;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Full-track stitch: track[src][s0 + m] += w(m) * seg[src][b][m] (oracle/stitch.py; new
+// behaviour).  Periodic-Hann cross-fade, flat outer edges.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) segment_ola_kernel(const float* __restrict__ seg, int n_src, int batch,
+                                                          int seg_len, int seg_index0, int n_seg_total,
+                                                          float* __restrict__ track, long long n_track) {
+  const int b = blockIdx.y, src = blockIdx.z;
+  const int gi = seg_index0 + b;
+  const long long start = (long long)gi * (seg_len >> 1);
+  const float* in = seg + ((size_t)src * batch + b) * seg_len;
+  float* out = track + (size_t)src * n_track;
+  const int half = seg_len >> 1;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < seg_len; m += gridDim.x * blockDim.x) {
+    const long long t = start + m;
+    if (t >= n_track) break;
+    float w = 0.5f - 0.5f * cospif(2.0f * (float)m / (float)seg_len);
+    if ((gi == 0 && m < half) || (gi == n_seg_total - 1 && m >= half)) w = 1.f;
+    atomicAdd(&out[t], w * in[m]);  // two addends per sample at most: order-independent in fp32
+  }
+}
+
+}  // namespace tfl

@@ -1,0 +1,519 @@
+// C ABI (include/tfl.h) of the B200-native TF-Locoformer forward path: plan / weight
+// packing / workspace planning and the launch sequences.  Host side only; kernels live in
+// kernels_f32.cuh (CUDA-core fp32 + bandwidth-bound stages) and kernels_tc.cuh (tcgen05).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels_f32.cuh"
+#include "kernels_tc.cuh"
+
+namespace tfl {
+
+static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+// ---- generic strided-permute copy used by the weight packer ---------------------------
+struct Permute {
+  int n[4]; long long s[4]; long long offset; int last_valid;
+};
+__global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, Permute p) {
+  const long long total = (long long)p.n[0] * p.n[1] * p.n[2] * p.n[3];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int i3 = (int)(r % p.n[3]); r /= p.n[3];
+    const int i2 = (int)(r % p.n[2]); r /= p.n[2];
+    const int i1 = (int)(r % p.n[1]); r /= p.n[1];
+    const int i0 = (int)r;
+    dst[i] = (i3 < p.last_valid) ? src[p.offset + i0 * p.s[0] + i1 * p.s[1] + i2 * p.s[2] + i3 * p.s[3]] : 0.f;
+  }
+}
+static void permute(const float* src, float* dst, int n0, int n1, int n2, int n3, long long s0, long long s1,
+                    long long s2, long long s3, long long offset, int last_valid, cudaStream_t st) {
+  Permute p{{n0, n1, n2, n3}, {s0, s1, s2, s3}, offset, last_valid < 0 ? n3 : last_valid};
+  const long long total = (long long)n0 * n1 * n2 * n3;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  permute_kernel<<<blocks, 256, 0, st>>>(src, dst, p);
+}
+
+__global__ void fft_tables_kernel(float2* tw, float* win, int n_fft) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_fft / 2) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)n_fft, &s, &c);
+    tw[i] = make_float2((float)c, (float)s);
+  }
+  if (i < n_fft) win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)n_fft));
+}
+
+// ---- packed layout --------------------------------------------------------------------
+static void build_layout(tfl_plan* pl) {
+  const tfl_config& c = pl->cfg;
+  PackLayout& L = pl->lay;
+  size_t off = 0;
+  auto take = [&](size_t n_float) { size_t o = off; off = align_up(off + n_float * sizeof(float)); return o; };
+  const int C = c.emb_dim, A = c.attention_dim, K = c.conv_kernel;
+  L.enc_w = L.enc_b = L.gln_w = L.gln_b = L.dec_w = L.dec_b = 0;
+  if (c.enc_in_ch > 0) {
+    L.enc_w = take((size_t)9 * c.enc_in_ch * C); L.enc_b = take(C); L.gln_w = take(C); L.gln_b = take(C);
+    L.dec_w = take((size_t)9 * C * 8); L.dec_b = take(8);
+  }
+  L.twiddle = L.window = 0;
+  if (c.n_fft > 0) { L.twiddle = take(c.n_fft); L.window = take(c.n_fft); }
+  L.paths.resize((size_t)c.n_layers * 2);
+  for (auto& p : L.paths) {
+    for (int j = 0; j < pl->n_ffn; ++j) {
+      FfnPack& f = p.ffn[j];
+      f.hidden = j == 0 ? c.ffn_hidden0 : c.ffn_hidden1;
+      f.gamma = take(C);
+      f.w1 = take((size_t)K * C * 2 * f.hidden); f.b1 = take(2 * f.hidden);
+      f.w2 = take((size_t)K * f.hidden * C); f.b2 = take(C);
+      f.tc = take(tc_ffn_image_bytes(C, f.hidden, K) / sizeof(float));
+    }
+    p.attn_gamma = take(C);
+    p.rope = take(pl->head_dim / 2 + 1);
+    p.wqkv = take((size_t)C * 3 * A);
+    p.wo = take((size_t)A * C);
+    p.tc_qkv = p.tc_wo = 0;
+  }
+  L.total = off;
+}
+
+}  // namespace tfl
+
+using namespace tfl;
+
+extern "C" {
+
+int tfl_version(void) { return 100; }
+const char* tfl_last_error(void) { return g_err; }
+uint64_t tfl_launch_count(void) { return g_launches; }
+
+int tfl_plan_create(const tfl_config* cfg, tfl_plan** out) {
+  TFL_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  const tfl_config& c = *cfg;
+  TFL_CHECK(c.emb_dim > 0 && c.emb_dim % 8 == 0, "emb_dim must be a positive multiple of 8 (got %d)", c.emb_dim);
+  TFL_CHECK(c.num_groups > 0 && c.emb_dim % c.num_groups == 0 && (c.emb_dim / c.num_groups) % 4 == 0,
+            "emb_dim/num_groups must be a multiple of 4 (emb_dim %d, groups %d)", c.emb_dim, c.num_groups);
+  TFL_CHECK(c.n_heads > 0 && c.attention_dim % c.n_heads == 0, "attention_dim %% n_heads != 0");
+  TFL_CHECK(c.attention_dim % 8 == 0, "attention_dim must be a multiple of 8");
+  const int hd = c.attention_dim / c.n_heads;
+  TFL_CHECK(hd % 2 == 0 && hd <= 64, "head_dim must be even and <= 64 (got %d)", hd);
+  TFL_CHECK(c.conv_kernel >= 1 && c.conv_kernel <= 16, "conv1d_kernel out of range");
+  TFL_CHECK(c.ffn_hidden0 > 0 && c.ffn_hidden0 % 8 == 0, "ffn_hidden_dim must be a multiple of 8");
+  TFL_CHECK(!c.macaron || (c.ffn_hidden1 > 0 && c.ffn_hidden1 % 8 == 0), "ffn_hidden_dim must be a multiple of 8");
+  TFL_CHECK(c.n_layers >= 1 && c.n_src >= 1, "n_layers / n_src must be >= 1");
+  TFL_CHECK(c.enc_in_ch == 0 || c.enc_in_ch == 2, "encoder conv supports 2 input channels (re, im)");
+  TFL_CHECK(c.enc_in_ch == 0 || c.n_src * 2 <= 8, "decoder supports up to 4 sources");
+  if (c.n_fft > 0) {
+    TFL_CHECK((c.n_fft & (c.n_fft - 1)) == 0 && c.n_fft >= 16 && c.n_fft <= 8192, "n_fft must be a power of two in [16, 8192]");
+    TFL_CHECK(c.hop > 0 && c.hop <= c.n_fft, "hop_length must be in (0, n_fft]");
+  }
+  tfl_plan* pl = new tfl_plan();
+  pl->cfg = c;
+  pl->head_dim = hd;
+  pl->n_ffn = c.macaron ? 2 : 1;
+  int dev = 0;
+  pl->sm_count = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) pl->sm_count = n;
+  }
+  (void)cudaGetLastError();
+  build_layout(pl);
+  *out = pl;
+  return 0;
+}
+
+void tfl_plan_destroy(tfl_plan* plan) { delete plan; }
+
+int tfl_num_weight_tensors(const tfl_plan* pl) {
+  const tfl_config& c = pl->cfg;
+  const int per_path = pl->n_ffn + 4 * pl->n_ffn + 1 + (c.rope ? 1 : 0) + 2;
+  return (c.enc_in_ch > 0 ? 6 : 0) + c.n_layers * 2 * per_path;
+}
+
+size_t tfl_packed_bytes(const tfl_plan* pl) { return pl->lay.total; }
+
+int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, void* packed, size_t packed_bytes,
+                     tfl_stream_t stream) {
+  TFL_CHECK(pl && w && packed, "null argument");
+  TFL_CHECK(n_weights == tfl_num_weight_tensors(pl), "expected %d weight tensors, got %d", tfl_num_weight_tensors(pl), n_weights);
+  TFL_CHECK(packed_bytes >= pl->lay.total, "packed buffer too small");
+  const tfl_config& c = pl->cfg;
+  const PackLayout& L = pl->lay;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)packed;
+  auto dst = [&](size_t off) { return (float*)(base + off); };
+  auto copy = [&](const float* src, size_t off, int n) { permute(src, dst(off), 1, 1, 1, n, 0, 0, 0, 1, 0, -1, st); };
+  const int C = c.emb_dim, A = c.attention_dim, K = c.conv_kernel, S2 = c.n_src * 2;
+  TFL_CUDA(cudaMemsetAsync(packed, 0, pl->lay.total, st));
+  int i = 0;
+  if (c.enc_in_ch > 0) {
+    const int ci = c.enc_in_ch;
+    // conv.0.weight [C, ci, 3, 3] -> [9][ci][C]
+    permute(w[i++], dst(L.enc_w), 1, 9, ci, C, 0, 1, 9, (long long)ci * 9, 0, -1, st);
+    copy(w[i++], L.enc_b, C); copy(w[i++], L.gln_w, C); copy(w[i++], L.gln_b, C);
+  }
+  for (int layer = 0; layer < c.n_layers; ++layer)
+    for (int axis = 0; axis < 2; ++axis) {
+      const PathPack& p = L.paths[(size_t)layer * 2 + axis];
+      for (int j = 0; j < pl->n_ffn; ++j) copy(w[i++], p.ffn[j].gamma, C);
+      for (int j = 0; j < pl->n_ffn; ++j) {
+        const FfnPack& f = p.ffn[j];
+        const int H = f.hidden;
+        const float* w1 = w[i++]; const float* b1 = w[i++]; const float* w2 = w[i++]; const float* b2 = w[i++];
+        // conv1d.weight [2H, C, K] -> [K][C][H][2] (value, gate interleaved)
+        permute(w1, dst(f.w1), K, C, H, 2, 1, K, (long long)C * K, (long long)H * C * K, 0, -1, st);
+        permute(b1, dst(f.b1), 1, 1, H, 2, 0, 0, 1, H, 0, -1, st);
+        // deconv1d.weight [H, C, K] -> [K'][H][C] with k = K-1-k'
+        permute(w2, dst(f.w2), 1, K, H, C, 0, -1, (long long)C * K, K, K - 1, -1, st);
+        copy(b2, f.b2, C);
+        TFL_CHECK(tc_pack_ffn(w1, b1, w2, b2, (char*)packed + f.tc, C, H, K, st) == 0, "tc_pack_ffn failed");
+      }
+      copy(w[i++], p.attn_gamma, C);
+      if (c.rope) copy(w[i++], p.rope, pl->head_dim / 2);
+      permute(w[i++], dst(p.wqkv), 1, 1, C, 3 * A, 0, 0, 1, C, 0, -1, st);  // [3A, C] -> [C][3A]
+      permute(w[i++], dst(p.wo), 1, 1, A, C, 0, 0, 1, A, 0, -1, st);        // [C, A] -> [A][C]
+    }
+  if (c.enc_in_ch > 0) {
+    // deconv.weight [C, 2S, 3, 3] -> [9][C][8]
+    permute(w[i++], dst(L.dec_w), 1, 9, C, 8, 0, 1, (long long)S2 * 9, 9, 0, S2, st);
+    copy(w[i++], L.dec_b, S2);
+  }
+  if (c.n_fft > 0)
+    fft_tables_kernel<<<(c.n_fft + 255) / 256, 256, 0, st>>>((float2*)(base + L.twiddle), dst(L.window), c.n_fft);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- workspace ------------------------------------------------------------------------
+namespace tfl {
+struct Workspace {
+  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, tc, total;
+  int gln_blocks;
+};
+static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int precision) {
+  const tfl_config& c = pl->cfg;
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t N = (size_t)B * Tf * F;
+  const int C = c.emb_dim, A = c.attention_dim, K = c.conv_kernel;
+  const int Hmax = c.ffn_hidden0 > c.ffn_hidden1 ? c.ffn_hidden0 : c.ffn_hidden1;
+  w.spec = take(N * 2 * sizeof(float));
+  w.x = take(N * C * sizeof(float));
+  w.est = take(N * 2 * c.n_src * sizeof(float));
+  w.gln_blocks = pl->sm_count * 2;
+  w.gln_part = take((size_t)B * w.gln_blocks * 2 * sizeof(double));
+  w.gln_stats = take((size_t)B * 2 * sizeof(float));
+  w.xn = take(N * C * sizeof(float));
+  const size_t hid_rows_f = (size_t)B * Tf * (F + K - 1), hid_rows_t = (size_t)B * F * (Tf + K - 1);
+  const size_t hid_rows = hid_rows_f > hid_rows_t ? hid_rows_f : hid_rows_t;
+  if (precision == TFL_PRECISION_FP32) w.hid = take(hid_rows * Hmax * sizeof(float));
+  w.qkv = take(N * 3 * A * sizeof(float));
+  w.o = take(N * A * sizeof(float));
+  w.tc = take(tc_workspace_bytes(pl, B, Tf, F));
+  w.total = off;
+  return w;
+}
+
+static int norm_launch(const float* x, float* y, long long rows, int C, int G, const float* gamma, float eps,
+                       int sm_count, cudaStream_t st) {
+  const int lanes = (C / G) / 4;
+  int W = 1;
+  while (W < lanes) W <<= 1;
+  TFL_CHECK(W <= 32, "emb_dim/num_groups > 128 is not supported");
+  const long long pairs = rows * G;
+  const long long per_block = 256 / W;
+  long long blocks = (pairs + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define NORM_CASE(w) case w: rms_group_norm_kernel<w, float><<<(int)blocks, 256, 0, st>>>(x, y, rows, C, G, gamma, eps); break;
+  switch (W) { NORM_CASE(1) NORM_CASE(2) NORM_CASE(4) NORM_CASE(8) NORM_CASE(16) NORM_CASE(32) }
+#undef NORM_CASE
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class Epi>
+static int gemm_launch(const TapGemm& g, const Epi& epi, cudaStream_t st) {
+  TFL_CHECK(g.Kc % GBK == 0 && g.N % 4 == 0, "tap-GEMM needs Kc %% 8 == 0 and N %% 4 == 0 (Kc %d N %d)", g.Kc, g.N);
+  dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
+  tap_gemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+struct Dims { int B, Tf, F; };
+
+static int ffn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, int j, float* x, Dims d,
+                   const Workspace& ws, char* wsp, cudaStream_t st) {
+  const tfl_config& c = pl->cfg;
+  const FfnPack& f = pl->lay.paths[(size_t)layer * 2 + axis].ffn[j];
+  const int C = c.emb_dim, K = c.conv_kernel, H = f.hidden;
+  const int S = axis == TFL_AXIS_FREQ ? d.F : d.Tf;
+  const int nseq = axis == TFL_AXIS_FREQ ? d.B * d.Tf : d.B * d.F;
+  const long long rows = (long long)d.B * d.Tf * d.F;
+  float* xn = (float*)(wsp + ws.xn);
+  float* hid = (float*)(wsp + ws.hid);
+  if (norm_launch(x, xn, rows, C, c.num_groups, (const float*)(packed + f.gamma), c.eps, pl->sm_count, st)) return -1;
+  const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
+  TapGemm g1{xn, xmap, S, S + K - 1, K - 1, K, C, (const float*)(packed + f.w1), (const float*)(packed + f.b1),
+             2 * H, (long long)nseq * (S + K - 1)};
+  if (gemm_launch(g1, EpiSwiGLU{hid, H}, st)) return -1;
+  TapGemm g2{hid, make_dense_map((long long)(S + K - 1) * H, H), S + K - 1, S, 0, K, H,
+             (const float*)(packed + f.w2), (const float*)(packed + f.b2), C, (long long)nseq * S};
+  return gemm_launch(g2, EpiResidual{x, xmap}, st);
+}
+
+static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
+                    const Workspace& ws, char* wsp, cudaStream_t st) {
+  const tfl_config& c = pl->cfg;
+  const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
+  const int C = c.emb_dim, A = c.attention_dim, hd = pl->head_dim, heads = c.n_heads;
+  const int L = axis == TFL_AXIS_FREQ ? d.F : d.Tf;
+  const int nseq = axis == TFL_AXIS_FREQ ? d.B * d.Tf : d.B * d.F;
+  const long long rows = (long long)d.B * d.Tf * d.F;
+  float* xn = (float*)(wsp + ws.xn);
+  float* qkv = (float*)(wsp + ws.qkv);
+  float* o = (float*)(wsp + ws.o);
+  if (norm_launch(x, xn, rows, C, c.num_groups, (const float*)(packed + p.attn_gamma), c.eps, pl->sm_count, st)) return -1;
+  const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
+  TapGemm g1{xn, xmap, L, L, 0, 1, C, (const float*)(packed + p.wqkv), nullptr, 3 * A, (long long)nseq * L};
+  EpiQkvRope e1{qkv, A, hd, heads, L, nseq, c.rope ? (const float*)(packed + p.rope) : nullptr};
+  if (gemm_launch(g1, e1, st)) return -1;
+  const size_t per = (size_t)nseq * heads * L * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  dim3 grid((L + 127) / 128, heads, nseq);
+#define ATT_CASE(HD) attn_f32_kernel<HD><<<grid, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale)
+  if (hd <= 8) ATT_CASE(8); else if (hd <= 16) ATT_CASE(16); else if (hd <= 32) ATT_CASE(32); else ATT_CASE(64);
+#undef ATT_CASE
+  TFL_LAUNCH_CHECK();
+  TapGemm g2{o, make_dense_map((long long)L * A, A), L, L, 0, 1, A, (const float*)(packed + p.wo), nullptr, C,
+             (long long)nseq * L};
+  return gemm_launch(g2, EpiResidual{x, xmap}, st);
+}
+
+static int path_forward(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
+                        const Workspace& ws, char* wsp, int precision, cudaStream_t st) {
+  // LocoformerBlock.forward, models/mss_tflocoformer.py:430-464
+  if (precision == TFL_PRECISION_BF16) return tc_path_forward(pl, packed, layer, axis, x, d.B, d.Tf, d.F, wsp + ws.tc, wsp, ws.xn, ws.qkv, ws.o, st);
+  if (pl->cfg.macaron && ffn_f32(pl, packed, layer, axis, 1, x, d, ws, wsp, st)) return -1;
+  if (attn_f32(pl, packed, layer, axis, x, d, ws, wsp, st)) return -1;
+  return ffn_f32(pl, packed, layer, axis, 0, x, d, ws, wsp, st);
+}
+
+static int blocks_forward(const tfl_plan* pl, const char* packed, float* x, Dims d, const Workspace& ws, char* wsp,
+                          int precision, cudaStream_t st) {
+  for (int layer = 0; layer < pl->cfg.n_layers; ++layer) {
+    const int first = pl->cfg.tf_order == 0 ? TFL_AXIS_FREQ : TFL_AXIS_TIME;  // :332-353
+    if (path_forward(pl, packed, layer, first, x, d, ws, wsp, precision, st)) return -1;
+    if (path_forward(pl, packed, layer, 1 - first, x, d, ws, wsp, precision, st)) return -1;
+  }
+  return 0;
+}
+
+static int check_common(const tfl_plan* pl, const void* packed, int B, int Tf, int F, int precision) {
+  TFL_CHECK(pl != nullptr && packed != nullptr, "null plan / packed weights");
+  TFL_CHECK(B >= 1 && Tf >= 1 && F >= 1, "empty input (batch %d, frames %d, bins %d)", B, Tf, F);
+  TFL_CHECK(precision == TFL_PRECISION_FP32 || precision == TFL_PRECISION_BF16, "unknown precision %d", precision);
+  return 0;
+}
+}  // namespace tfl
+
+extern "C" {
+
+size_t tfl_workspace_bytes(const tfl_plan* pl, int B, int Tf, int F, int precision) {
+  return plan_workspace(pl, B, Tf, F, precision).total;
+}
+
+int tfl_stft(const tfl_plan* pl, const void* packed, const float* audio, int B, int T, float* spec, tfl_stream_t stream) {
+  TFL_CHECK(pl && packed && audio && spec, "null argument");
+  const tfl_config& c = pl->cfg;
+  TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
+  TFL_CHECK(B >= 1, "empty batch");
+  TFL_CHECK(T > c.n_fft / 2, "reflect padding needs more than n_fft/2 = %d samples (got %d)", c.n_fft / 2, T);
+  const int Tf = 1 + T / c.hop;
+  const char* base = (const char*)packed;
+  stft_kernel<<<dim3(Tf, B), 256, c.n_fft * sizeof(float2), (cudaStream_t)stream>>>(
+      audio, T, c.n_fft, ilog2(c.n_fft), c.hop, Tf, (const float2*)(base + pl->lay.twiddle),
+      (const float*)(base + pl->lay.window), spec);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, int B, int Tf, int F, float* x,
+                     void* workspace, size_t ws_bytes, tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, 0)) return -1;
+  TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv encoder");
+  const Workspace ws = plan_workspace(pl, B, Tf, F, 0);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  const tfl_config& c = pl->cfg;
+  const char* base = (const char*)packed;
+  char* wsp = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = c.emb_dim;
+  double* part = (double*)(wsp + ws.gln_part);
+  float* stats = (float*)(wsp + ws.gln_stats);
+  const size_t smem = ((size_t)9 * 2 * C + C) * sizeof(float);
+  enc_conv_kernel<2><<<dim3(ws.gln_blocks, B), 256, smem, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
+                                                              (const float*)(base + pl->lay.enc_b), x, part);
+  TFL_LAUNCH_CHECK();
+  gln_finalize_kernel<<<B, 256, 0, st>>>(part, ws.gln_blocks, (double)Tf * F * C, c.eps, stats);
+  TFL_LAUNCH_CHECK();
+  gln_apply_kernel<<<dim3(pl->sm_count * 4, B), 256, 0, st>>>(x, (long long)Tf * F * C / 4, C, stats,
+                                                            (const float*)(base + pl->lay.gln_w),
+                                                            (const float*)(base + pl->lay.gln_b));
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_rms_group_norm(const tfl_plan* pl, const void* packed, int layer, int axis, int which, const float* x,
+                       float* y, int64_t rows, tfl_stream_t stream) {
+  TFL_CHECK(pl && packed && x && y, "null argument");
+  TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer/axis");
+  TFL_CHECK(which == 2 || (which >= 0 && which < pl->n_ffn), "bad norm selector %d", which);
+  if (rows == 0) return 0;
+  const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
+  const size_t goff = which == 2 ? p.attn_gamma : p.ffn[which].gamma;
+  return norm_launch(x, y, rows, pl->cfg.emb_dim, pl->cfg.num_groups, (const float*)((const char*)packed + goff),
+                     pl->cfg.eps, pl->sm_count, (cudaStream_t)stream);
+}
+
+int tfl_conv_swiglu_ffn(const tfl_plan* pl, const void* packed, int layer, int axis, int ffn_index, float* x, int B,
+                        int Tf, int F, void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer/axis");
+  TFL_CHECK(ffn_index >= 0 && ffn_index < pl->n_ffn, "bad ffn index %d", ffn_index);
+  const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  if (precision == TFL_PRECISION_BF16)
+    return tc_ffn(pl, (const char*)packed, layer, axis, ffn_index, x, B, Tf, F, (char*)workspace + ws.tc,
+                  (cudaStream_t)stream);
+  return ffn_f32(pl, (const char*)packed, layer, axis, ffn_index, x, Dims{B, Tf, F}, ws, (char*)workspace,
+                 (cudaStream_t)stream);
+}
+
+int tfl_rope_attn(const tfl_plan* pl, const void* packed, int layer, int axis, float* x, int B, int Tf, int F,
+                  void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer/axis");
+  const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  if (precision == TFL_PRECISION_BF16)
+    return tc_attn(pl, (const char*)packed, layer, axis, x, B, Tf, F, (char*)workspace + ws.tc, (char*)workspace,
+                   ws.xn, ws.qkv, ws.o, (cudaStream_t)stream);
+  return attn_f32(pl, (const char*)packed, layer, axis, x, Dims{B, Tf, F}, ws, (char*)workspace, (cudaStream_t)stream);
+}
+
+int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, int Tf, int F, float* est,
+                 tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, 0)) return -1;
+  TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv decoder");
+  const int C = pl->cfg.emb_dim;
+  const size_t smem = (size_t)9 * C * 8 * sizeof(float);
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TFL_CUDA(cudaFuncSetAttribute(dec_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const long long n_pos = (long long)B * Tf * F;
+  const char* base = (const char*)packed;
+  long long blocks = (n_pos + 7) / 8;
+  if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
+  dec_conv_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, Tf, F, C, pl->cfg.n_src * 2,
+                                                                   (const float*)(base + pl->lay.dec_w),
+                                                                   (const float*)(base + pl->lay.dec_b), est, n_pos);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_istft_ola(const tfl_plan* pl, const void* packed, const float* est, int B, int Tf, int T, float* audio,
+                  tfl_stream_t stream) {
+  TFL_CHECK(pl && packed && est && audio, "null argument");
+  const tfl_config& c = pl->cfg;
+  TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
+  TFL_CHECK(B >= 1 && Tf >= 1 && T >= 1, "empty input");
+  const char* base = (const char*)packed;
+  const size_t smem = (size_t)c.n_fft * sizeof(float2) + (size_t)2 * c.hop * sizeof(float);
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TFL_CUDA(cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid((T + c.hop - 1) / c.hop, c.n_src, B);
+  istft_ola_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(est, c.n_src, Tf, c.n_fft, ilog2(c.n_fft), c.hop, T,
+                                                              (const float2*)(base + pl->lay.twiddle),
+                                                              (const float*)(base + pl->lay.window), audio, B);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_blocks(const tfl_plan* pl, const void* packed, float* x, int B, int Tf, int F, void* workspace,
+               size_t ws_bytes, int precision, tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  return blocks_forward(pl, (const char*)packed, x, Dims{B, Tf, F}, ws, (char*)workspace, precision,
+                        (cudaStream_t)stream);
+}
+
+int tfl_separator_forward(const tfl_plan* pl, const void* packed, const float* spec, int B, int Tf, int F, float* est,
+                          void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  TFL_CHECK(spec && est, "null argument");
+  const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  char* wsp = (char*)workspace;
+  float* x = (float*)(wsp + ws.x);
+  if (tfl_enc_conv_gln(pl, packed, spec, B, Tf, F, x, workspace, ws_bytes, stream)) return -1;
+  if (blocks_forward(pl, (const char*)packed, x, Dims{B, Tf, F}, ws, wsp, precision, (cudaStream_t)stream)) return -1;
+  return tfl_dec_conv(pl, packed, x, B, Tf, F, est, stream);
+}
+
+int tfl_forward(const tfl_plan* pl, const void* packed, const float* mixture, int B, int T, float* audio,
+                float* est_spec, void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
+  TFL_CHECK(pl && packed && mixture, "null argument");
+  const tfl_config& c = pl->cfg;
+  TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
+  TFL_CHECK(B >= 1, "empty batch");
+  TFL_CHECK(T > c.n_fft / 2, "reflect padding needs more than n_fft/2 = %d samples (got %d)", c.n_fft / 2, T);
+  const int Tf = 1 + T / c.hop, F = c.n_fft / 2 + 1;
+  const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  char* wsp = (char*)workspace;
+  float* spec = (float*)(wsp + ws.spec);
+  float* est = est_spec != nullptr ? est_spec : (float*)(wsp + ws.est);
+  if (tfl_stft(pl, packed, mixture, B, T, spec, stream)) return -1;
+  if (tfl_separator_forward(pl, packed, spec, B, Tf, F, est, workspace, ws_bytes, precision, stream)) return -1;
+  if (audio != nullptr) return tfl_istft_ola(pl, packed, est, B, Tf, T, audio, stream);
+  return 0;
+}
+
+int tfl_segment_ola(const float* seg_audio, int n_src, int B, int seg_len, int seg_index0, int n_seg_total,
+                    float* track, int64_t n_track, tfl_stream_t stream) {
+  TFL_CHECK(seg_audio && track, "null argument");
+  TFL_CHECK(n_src >= 1 && B >= 1 && seg_len >= 2 && seg_len % 2 == 0, "bad segment shape");
+  TFL_CHECK(seg_index0 >= 0 && seg_index0 + B <= n_seg_total, "segment index out of range");
+  dim3 grid((seg_len + 255) / 256 < 296 ? (seg_len + 255) / 256 : 296, B, n_src);
+  segment_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seg_audio, n_src, B, seg_len, seg_index0, n_seg_total,
+                                                             track, n_track);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

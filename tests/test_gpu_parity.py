@@ -1,0 +1,208 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the committed
+reference vectors.  fp32 mode: max-abs <= 1e-4 and SI-SDR >= 70 dB; bf16 mode: SI-SDR >= 40 dB
+(BASELINE.json north_star).  Run on the B200 box with ``pytest -m gpu``.
+"""
+import math
+
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+FP32_MAXABS = 1e-4
+FP32_SISDR = 70.0
+BF16_SISDR = 40.0
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import mss_tf_locoformer_b200 as m
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return m
+
+
+def _check(got, ref, maxabs=FP32_MAXABS, sisdr=FP32_SISDR, what=""):
+    got, ref = got.detach().cpu(), ref.detach().cpu()
+    if got.is_complex():
+        got, ref = torch.view_as_real(got.contiguous()), torch.view_as_real(ref.contiguous())
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = float((got - ref).abs().max())
+    sd = oracle.si_sdr_db(got, ref)
+    assert err <= maxabs, f"{what}: max-abs {err:.3e} > {maxabs}"
+    assert sd >= sisdr, f"{what}: SI-SDR {sd:.1f} dB < {sisdr}"
+    return err, sd
+
+
+def _mss(pkg, name, precision="fp32"):
+    cfg, sd, arr = load_golden(name)
+    model = pkg.TFLocoformerMSS(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    model.precision = precision
+    return cfg, sd, arr, model
+
+
+@pytest.mark.parametrize("name", ["mss_hop2_macaron", "mss_hop4_single_tf"])
+def test_mss_forward_golden_fp32(pkg, name):
+    cfg, sd, arr, model = _mss(pkg, name)
+    with torch.no_grad():
+        out = model(arr["mixture"].cuda())
+    assert list(out.keys()) == oracle.locoformer_oracle.SOURCE_NAMES[: cfg["n_sources"]]
+    for k, v in out.items():
+        _check(v, arr["out/" + k], what=f"{name}/{k}")
+    if cfg["n_sources"] >= 4:
+        with torch.no_grad():
+            sp = model(arr["mixture"].cuda(), return_time_domain=False)
+        for k, v in sp.items():
+            assert v.shape == arr["spec/" + k].shape
+            _check(v, arr["spec/" + k], maxabs=5e-4, what=f"{name}/spec/{k}")
+
+
+@pytest.mark.parametrize("name", ["sep_rope_k4", "sep_nope_k1", "sep_rope_k8"])
+def test_separator_golden_fp32(pkg, name):
+    cfg, sd, arr = load_golden(name)
+    model = pkg.TFLocoformerSeparator(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(arr["spec_in"].cuda())
+        out4 = model(arr["spec_in"].cuda().unsqueeze(1))
+    _check(out, arr["spec_out"], maxabs=2e-4, what=name)
+    assert torch.equal(out, out4)
+
+
+def test_stage_kernels_fp32(pkg):
+    """Each stage entry point of include/tfl.h against the reference's own stage outputs."""
+    cfg, sd, arr, model = _mss(pkg, "mss_hop2_macaron")
+    eng = model._ready()
+    mix = arr["mixture"].cuda()
+    # K1 stft: [B, Tf, F, 2] vs torch.stft of the reference [B, F, Tf]
+    spec = eng.stft(mix)
+    ref = torch.view_as_real(arr["stft"].transpose(1, 2).contiguous())
+    _check(spec, ref, maxabs=2e-4, sisdr=100.0, what="stft")
+    got_c = model.transform.stft(mix)
+    assert got_c.shape == arr["stft"].shape
+    # K7 istft: round trip of the reference STFT back to the mixture
+    est = ref.cuda().unsqueeze(1).expand(-1, cfg["n_sources"], -1, -1, -1).contiguous()
+    aud = eng.istft(est, mix.shape[-1])
+    want = oracle.istft(arr["stft"].transpose(1, 2), cfg["n_fft"], cfg["hop_length"], mix.shape[-1])
+    for s in range(cfg["n_sources"]):
+        _check(aud[s], want, maxabs=2e-5, sisdr=100.0, what="istft")
+    # K2 encoder + gLN
+    x = eng.enc_conv_gln(ref.cuda())
+    enc_ref = arr["stage/conv:out"].permute(0, 2, 3, 1)
+    _check(x, enc_ref, maxabs=5e-5, what="enc_conv_gln")
+    # K3 rms group norm (layer 0, freq path, attn_norm)
+    nin, nout = arr["stage/blocks.0.freq_path.attn_norm:in"], arr["stage/blocks.0.freq_path.attn_norm:out"]
+    _check(eng.rms_group_norm(0, 0, 2, nin.cuda()), nout, maxabs=2e-5, what="rms_group_norm")
+    _check(model.blocks[0].freq_path.attn_norm(nin.cuda()), nout, maxabs=2e-5, what="RMSGroupNorm.forward")
+    # K5 attention (+norm +residual): x + attn(norm(x))
+    want = nin + arr["stage/blocks.0.freq_path.attn:out"].reshape(nin.shape)
+    _check(eng.attn_(0, 0, nin.cuda().clone(), 0), want, maxabs=5e-5, what="rope_attn")
+    # K4 FFN on both axes vs the oracle
+    xin = enc_ref.contiguous()
+    for axis, path in ((0, "freq_path"), (1, "frame_path")):
+        for j in (0, 1):
+            p = f"blocks.0.{path}"
+            xa = xin if axis == 0 else xin.transpose(1, 2).contiguous()
+            b, s1, s2, c = xa.shape
+            xn = oracle.rms_group_norm(xa, sd[f"{p}.ffn_norm.{j}.gamma"], cfg["num_groups"], cfg["eps"])
+            y = oracle.swiglu_conv_deconv(xn.reshape(b * s1, s2, c), sd[f"{p}.ffn.{j}.conv1d.weight"],
+                                          sd[f"{p}.ffn.{j}.conv1d.bias"], sd[f"{p}.ffn.{j}.deconv1d.weight"],
+                                          sd[f"{p}.ffn.{j}.deconv1d.bias"]).reshape(xa.shape) + xa
+            want = y if axis == 0 else y.transpose(1, 2)
+            _check(eng.ffn_(0, axis, j, xin.cuda().clone(), 0), want, maxabs=5e-5, what=f"ffn axis{axis} j{j}")
+    # whole block through the module surface: [B, C, T, F] in / out
+    blk = model.blocks[0](arr["stage/conv:out"].cuda())
+    _check(blk, arr["stage/blocks.0:out"], maxabs=1e-4, what="TFLocoformerBlock.forward")
+    # K6 decoder
+    xfin = oracle.blocks_forward(enc_ref.contiguous(), sd, cfg)
+    dec = eng.dec_conv(xfin.cuda())                                  # [B, S, Tf, F, 2]
+    want = arr["stage/deconv:out"].permute(0, 2, 3, 1)               # [B, Tf, F, 2S]
+    b, tf, f, _ = want.shape
+    want = want.reshape(b, tf, f, -1, 2).permute(0, 3, 1, 2, 4)
+    _check(dec, want, maxabs=1e-4, what="dec_conv")
+
+
+def _random_model(pkg, cfg, seed=0):
+    torch.manual_seed(seed)
+    model = pkg.TFLocoformerMSS(**cfg).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.ndim == 1 and not n.endswith("rope.freqs"):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    return model
+
+
+def _mixture(n, batch, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n) / 44100.0
+    x = 0.1 * torch.randn(batch, n, generator=g)
+    for f0 in (55.0, 220.0, 880.0, 3520.0, 7040.0):
+        x = x + 0.05 * torch.sin(2 * math.pi * f0 * t)[None]
+    return x.clamp(-1, 1)
+
+
+VARIANT_D = dict(n_fft=2048, hop_length=1024, n_sources=4, n_layers=1, emb_dim=128, norm_type="rmsgroupnorm",
+                 num_groups=4, tf_order="ft", n_heads=4, flash_attention=True, attention_dim=128, pos_enc="rope",
+                 ffn_type=["swiglu_conv1d", "swiglu_conv1d"], ffn_hidden_dim=[384, 384], conv1d_kernel=4,
+                 conv1d_shift=1, dropout=0.0, eps=1e-5)
+VARIANT_Y = dict(VARIANT_D, hop_length=512, emb_dim=96, attention_dim=96)
+VARIANT_SMALL = dict(VARIANT_D, n_fft=1024, hop_length=256, emb_dim=48, attention_dim=48, ffn_hidden_dim=[192, 192])
+
+
+@pytest.mark.parametrize("name,cfg,n_samples", [("D", VARIANT_D, 30000), ("Y", VARIANT_Y, 20000),
+                                                 ("small", VARIANT_SMALL, 12000)])
+def test_real_width_one_layer_fp32(pkg, name, cfg, n_samples):
+    """Production channel widths (one layer, ~0.5 s audio) against the live oracle."""
+    model = _random_model(pkg, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    mix = _mixture(n_samples, 1)
+    ocfg = dict(cfg)
+    want = oracle.mss_forward(sd, ocfg, mix)
+    model = model.cuda()
+    model.precision = "fp32"
+    with torch.no_grad():
+        got = model(mix.cuda())
+    for k in want:
+        _check(got[k], want[k], what=f"{name}/{k}")
+
+
+def test_batch_rows_are_independent(pkg):
+    """Size-independent property: a batch of segments equals the segments run one by one, bit for bit."""
+    cfg, sd, arr, model = _mss(pkg, "mss_hop2_macaron")
+    mix = torch.cat([arr["mixture"], arr["mixture"].flip(0) * 0.5], 0).cuda()
+    with torch.no_grad():
+        full = model(mix)
+        for b in range(mix.shape[0]):
+            one = model(mix[b:b + 1])
+            for k in full:
+                assert torch.equal(full[k][b], one[k][0]), (k, b)
+
+
+def test_errors(pkg):
+    cfg, sd, arr, model = _mss(pkg, "mss_hop2_macaron")
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, cfg["n_fft"] // 2, device="cuda"))          # reflect pad too large, as torch.stft
+    with pytest.raises(RuntimeError):
+        model(arr["mixture"])                                             # CPU tensor: no CPU path
+    model.precision = "fp16"
+    with pytest.raises(ValueError):
+        model(arr["mixture"].cuda())
+
+
+def test_segment_ola_matches_oracle(pkg):
+    seg_len, n_src, n = 512, 3, 1700
+    starts = oracle.segment_starts(n, seg_len)
+    g = torch.Generator().manual_seed(5)
+    seg = torch.randn(len(starts), n_src, seg_len, generator=g)
+    want = oracle.stitch_segments(seg, n)
+    track = torch.zeros(n_src, n, device="cuda")
+    for i0 in range(0, len(starts), 2):                                  # batches of 2 segments, [S, B, L]
+        chunk = seg[i0:i0 + 2].permute(1, 0, 2).contiguous().cuda()
+        pkg.segment_ola(chunk, i0, len(starts), track)
+    _check(track, want, maxabs=1e-5, sisdr=100.0, what="segment_ola")
