@@ -115,6 +115,13 @@ int tfl_separator_forward(const tfl_plan* plan, const void* packed, const float*
 int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, int seg_index0,
                     int n_seg_total, float* track, int64_t n_track, tfl_stream_t stream);
 
+/* Diagnostic: exercises the tcgen05 plumbing of the bf16 path on one 128-row tile.
+ * mode 0: D[128, N] = sum_{tap < taps} A[m + tap, :] . B[tap][n, :]   A [128 + taps - 1, Kd], B [taps, N, Kd]
+ * mode 1: D[128, N] = A[m, :] . B[:, n]                               A [128, Kd], B [Kd, N] (N-contiguous)
+ * Operands are rounded to bf16, accumulation is fp32.  scratch: >= taps * N * Kd * 2 bytes. */
+int tfl_tc_selftest(const float* A, const float* B, float* D, void* scratch, int N, int Kd, int taps, int mode,
+                    tfl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

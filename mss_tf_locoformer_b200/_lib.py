@@ -40,6 +40,7 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),
     "tfl_separator_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _I, _P]),
     "tfl_segment_ola": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "tfl_tc_selftest": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 

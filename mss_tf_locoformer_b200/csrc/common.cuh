@@ -70,6 +70,7 @@ struct FfnPack {
   size_t gamma;      // [C] fp32
   size_t w1;         // fp32 [K][C][2H] with (value, gate) column-interleaved
   size_t b1;         // [2H] interleaved
+  size_t b1raw;      // [2H] reference order (value | gate), used by the tcgen05 epilogue
   size_t w2;         // fp32 [K][H][C], tap order reversed (tap k' multiplies g[i + k'])
   size_t b2;         // [C]
   size_t tc;         // bf16 tcgen05 image (0 = none)

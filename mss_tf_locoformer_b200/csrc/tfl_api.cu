@@ -76,7 +76,7 @@ static void build_layout(tfl_plan* pl) {
       FfnPack& f = p.ffn[j];
       f.hidden = j == 0 ? c.ffn_hidden0 : c.ffn_hidden1;
       f.gamma = take(C);
-      f.w1 = take((size_t)K * C * 2 * f.hidden); f.b1 = take(2 * f.hidden);
+      f.w1 = take((size_t)K * C * 2 * f.hidden); f.b1 = take(2 * f.hidden); f.b1raw = take(2 * f.hidden);
       f.w2 = take((size_t)K * f.hidden * C); f.b2 = take(C);
       f.tc = take(tc_ffn_image_bytes(C, f.hidden, K) / sizeof(float));
     }
@@ -176,6 +176,7 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
         // conv1d.weight [2H, C, K] -> [K][C][H][2] (value, gate interleaved)
         permute(w1, dst(f.w1), K, C, H, 2, 1, K, (long long)C * K, (long long)H * C * K, 0, -1, st);
         permute(b1, dst(f.b1), 1, 1, H, 2, 0, 0, 1, H, 0, -1, st);
+        copy(b1, f.b1raw, 2 * H);
         // deconv1d.weight [H, C, K] -> [K'][H][C] with k = K-1-k'
         permute(w2, dst(f.w2), 1, K, H, C, 0, -1, (long long)C * K, K, K - 1, -1, st);
         copy(b2, f.b2, C);
@@ -308,22 +309,33 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
   return gemm_launch(g2, EpiResidual{x, xmap}, st);
 }
 
-static int path_forward(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
+// LocoformerBlock.forward, models/mss_tflocoformer.py:430-464.  fp32: in place on *cur.  bf16: every fused
+// FFN kernel reads *cur and writes *alt (tile halos forbid in-place), after which the two swap.
+static int path_forward(const tfl_plan* pl, const char* packed, int layer, int axis, float** cur, float** alt, Dims d,
                         const Workspace& ws, char* wsp, int precision, cudaStream_t st) {
-  // LocoformerBlock.forward, models/mss_tflocoformer.py:430-464
-  if (precision == TFL_PRECISION_BF16) return tc_path_forward(pl, packed, layer, axis, x, d.B, d.Tf, d.F, wsp + ws.tc, wsp, ws.xn, ws.qkv, ws.o, st);
-  if (pl->cfg.macaron && ffn_f32(pl, packed, layer, axis, 1, x, d, ws, wsp, st)) return -1;
-  if (attn_f32(pl, packed, layer, axis, x, d, ws, wsp, st)) return -1;
-  return ffn_f32(pl, packed, layer, axis, 0, x, d, ws, wsp, st);
+  auto ffn = [&](int j) -> int {
+    if (precision == TFL_PRECISION_BF16) {
+      if (tc_ffn(pl, packed, layer, axis, j, *cur, *alt, d.B, d.Tf, d.F, st)) return -1;
+      float* t = *cur; *cur = *alt; *alt = t;
+      return 0;
+    }
+    return ffn_f32(pl, packed, layer, axis, j, *cur, d, ws, wsp, st);
+  };
+  if (pl->cfg.macaron && ffn(1)) return -1;
+  if (attn_f32(pl, packed, layer, axis, *cur, d, ws, wsp, st)) return -1;
+  return ffn(0);
 }
 
 static int blocks_forward(const tfl_plan* pl, const char* packed, float* x, Dims d, const Workspace& ws, char* wsp,
                           int precision, cudaStream_t st) {
+  float* cur = x;
+  float* alt = (float*)(wsp + ws.tc);
   for (int layer = 0; layer < pl->cfg.n_layers; ++layer) {
     const int first = pl->cfg.tf_order == 0 ? TFL_AXIS_FREQ : TFL_AXIS_TIME;  // :332-353
-    if (path_forward(pl, packed, layer, first, x, d, ws, wsp, precision, st)) return -1;
-    if (path_forward(pl, packed, layer, 1 - first, x, d, ws, wsp, precision, st)) return -1;
+    if (path_forward(pl, packed, layer, first, &cur, &alt, d, ws, wsp, precision, st)) return -1;
+    if (path_forward(pl, packed, layer, 1 - first, &cur, &alt, d, ws, wsp, precision, st)) return -1;
   }
+  TFL_CHECK(cur == x, "internal: residual ping-pong did not end in the caller's buffer");
   return 0;
 }
 
@@ -360,8 +372,8 @@ int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, 
                      void* workspace, size_t ws_bytes, tfl_stream_t stream) {
   if (check_common(pl, packed, B, Tf, F, 0)) return -1;
   TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv encoder");
-  const Workspace ws = plan_workspace(pl, B, Tf, F, 0);
-  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  const Workspace ws = plan_workspace(pl, B, Tf, F, 0);  // only the precision-independent prefix is used here
+  TFL_CHECK(workspace && ws_bytes >= ws.xn, "workspace too small (%zu < %zu)", ws_bytes, ws.xn);
   const tfl_config& c = pl->cfg;
   const char* base = (const char*)packed;
   char* wsp = (char*)workspace;
@@ -401,9 +413,13 @@ int tfl_conv_swiglu_ffn(const tfl_plan* pl, const void* packed, int layer, int a
   TFL_CHECK(ffn_index >= 0 && ffn_index < pl->n_ffn, "bad ffn index %d", ffn_index);
   const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
   TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
-  if (precision == TFL_PRECISION_BF16)
-    return tc_ffn(pl, (const char*)packed, layer, axis, ffn_index, x, B, Tf, F, (char*)workspace + ws.tc,
-                  (cudaStream_t)stream);
+  if (precision == TFL_PRECISION_BF16) {
+    float* y = (float*)((char*)workspace + ws.tc);
+    if (tc_ffn(pl, (const char*)packed, layer, axis, ffn_index, x, y, B, Tf, F, (cudaStream_t)stream)) return -1;
+    TFL_CUDA(cudaMemcpyAsync(x, y, (size_t)B * Tf * F * pl->cfg.emb_dim * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return 0;
+  }
   return ffn_f32(pl, (const char*)packed, layer, axis, ffn_index, x, Dims{B, Tf, F}, ws, (char*)workspace,
                  (cudaStream_t)stream);
 }
@@ -414,9 +430,6 @@ int tfl_rope_attn(const tfl_plan* pl, const void* packed, int layer, int axis, f
   TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer/axis");
   const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
   TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
-  if (precision == TFL_PRECISION_BF16)
-    return tc_attn(pl, (const char*)packed, layer, axis, x, B, Tf, F, (char*)workspace + ws.tc, (char*)workspace,
-                   ws.xn, ws.qkv, ws.o, (cudaStream_t)stream);
   return attn_f32(pl, (const char*)packed, layer, axis, x, Dims{B, Tf, F}, ws, (char*)workspace, (cudaStream_t)stream);
 }
 
@@ -514,6 +527,12 @@ int tfl_segment_ola(const float* seg_audio, int n_src, int B, int seg_len, int s
                                                              track, n_track);
   TFL_LAUNCH_CHECK();
   return 0;
+}
+
+int tfl_tc_selftest(const float* A, const float* B, float* D, void* scratch, int N, int Kd, int taps, int mode,
+                    tfl_stream_t stream) {
+  TFL_CHECK(A && B && D && scratch, "null argument");
+  return tc_selftest(A, B, D, scratch, N, Kd, taps, mode, (cudaStream_t)stream);
 }
 
 }  // extern "C"
