@@ -1,30 +1,37 @@
 // tcgen05 / TMEM kernels of TFL_PRECISION_BF16.
 //
-// K4  ffn_tc_kernel: x += ConvSwiGLU(RMSGroupNorm(x)) along one axis as ONE persistent,
+// K4  ffn_tc_kernel: y = x + ConvSwiGLU(RMSGroupNorm(x)) along one axis as ONE persistent,
 //     warp-specialised kernel (models/mss_tflocoformer.py:443-447,459-462 -> :626-655):
 //       producers   fp32 residual rows -> RMSGroupNorm -> bf16 chunk-major A tile in smem
 //       loader      weight stages (pre-packed bf16 smem images) via 1-D bulk async copies
 //       MMA thread  conv1d as KT row-shifted tcgen05.mma taps into TMEM (value | gate halves),
 //                   transposed conv as KT taps over the SwiGLU'd hidden tile
 //       epilogue    TMEM -> bias + SwiGLU -> bf16 hidden tile in smem (never touches HBM);
-//                   final: TMEM -> + bias + residual -> x (fp32)
+//                   final: TMEM -> + bias + residual -> y (fp32)
 //     Sequences are laid on a "stream" with period P = S + KT - 1 rows (KT - 1 shared zero rows
 //     between consecutive sequences == the reference's zero padding AFTER the norm, :640-644),
 //     so M tiles run across sequence boundaries and both axes use the same kernel through SeqMap.
+//     Each CTA works on NT = 2 M-tiles at once so every weight stage fetched from L2 feeds 256 rows.
+//
+//     TMEM (512 columns): D1[t] = 128 columns (64 value | 64 gate) per tile, D2[t] = C columns.
+//     Tensor-pipe order per hidden chunk c: M1[0](c) M1[1](c) M2[0](c-1) M2[1](c-1); the SwiGLU
+//     epilogue of chunk c overlaps M2(c-1) and M1(c+1).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace tfl {
 
-constexpr int TC_HC = 32;             // hidden channels per chunk (D1 tile = 2*HC TMEM columns)
+constexpr int TC_HC = 64;             // hidden channels per chunk (D1 tile = 2*HC TMEM columns)
 constexpr int TC_SMEM_MAX = 232448;   // 227 KB opt-in shared memory per CTA
 
 struct FfnTcGeom {
   int C, H, KT, G, NT, NS;            // NS = weight ring stages
   int AR;                             // rows per A / G tile = 128 + KT - 1
   int TS;                             // output rows per tile = 128 - (KT - 1)
-  int NC, KS;                         // hidden chunks, W2 stages per chunk
+  int NC;                             // hidden chunks
+  int KH;                             // K-halves per W1 tap stage (1 or 2)
+  int TPS, KS;                        // taps per W2 stage, W2 stages per chunk
   uint32_t stage_bytes, a_slot_bytes, g_buf_bytes;
   uint32_t off_a, off_g, off_w, off_tab, off_bar, smem_bytes;
   int threads;
@@ -35,13 +42,15 @@ inline bool ffn_tc_geometry(int C, int H, int KT, int G, FfnTcGeom* g) {
   g->C = C; g->H = H; g->KT = KT; g->G = G;
   g->NT = C <= 128 ? 2 : 1;
   g->AR = 128 + KT - 1; g->TS = 128 - (KT - 1);
-  g->NC = H / TC_HC; g->KS = (KT + 1) / 2;
-  g->stage_bytes = 128u * C;
+  g->NC = H / TC_HC;
+  g->KH = (C % 32 == 0) ? 2 : 1;
+  g->TPS = 2 / g->KH; g->KS = (KT + g->TPS - 1) / g->TPS;
+  g->stage_bytes = 256u * C / g->KH;
   g->a_slot_bytes = (uint32_t)(C / 8) * g->AR * 16;
   g->g_buf_bytes = (uint32_t)(TC_HC / 8) * g->AR * 16;
   uint32_t off = 0;
   g->off_a = off; off += (g->NT + 1) * g->a_slot_bytes;
-  g->off_g = off; off += g->NT * 2 * g->g_buf_bytes;
+  g->off_g = off; off += g->NT * g->g_buf_bytes;
   g->off_tab = off; off += (2 * H + 2 * C) * 4;
   off = (off + 15) & ~15u;
   g->off_bar = off; off += 512;
@@ -56,41 +65,45 @@ inline bool ffn_tc_geometry(int C, int H, int KT, int G, FfnTcGeom* g) {
 }
 
 inline size_t tc_ffn_image_bytes(int C, int H, int K) {
-  if (C % 16 != 0 || C > 256 || H % TC_HC != 0 || K < 1 || K > 8) return 0;
-  return (size_t)(H / TC_HC) * (K + (K + 1) / 2) * 128 * C;
+  FfnTcGeom g;
+  if (!ffn_tc_geometry(C, H, K, 1, &g)) return 0;
+  return (size_t)g.NC * (K * g.KH + g.KS) * g.stage_bytes;
 }
 
-// Weight image in consumption order: per hidden chunk c the KT conv1d tap stages W1(c, k)
-// (B operand [64 rows = 32 value | 32 gate] x [C], chunk-major), then -- one chunk late, matching
-// the MMA issue order -- the KS transposed-conv stages W2(c - 1, pair) (2 taps x [C rows] x [32]).
+// Weight image in consumption order.  Per hidden chunk c: the KT*KH conv1d stages W1(c, k, half)
+// (B operand [128 rows = 64 value | 64 gate] x [C/KH input channels], chunk-major) and then -- one
+// chunk late, matching the MMA issue order -- the KS transposed-conv stages W2(c - 1, s)
+// (TPS taps x [C rows] x [64 hidden channels]).
 __global__ void tc_pack_ffn_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                                   __nv_bfloat16* __restrict__ img, int C, int H, int KT) {
-  const int NC = H / TC_HC, KS = (KT + 1) / 2, n_per = KT + KS;
-  const long long stage_elems = 64LL * C;
+                                   __nv_bfloat16* __restrict__ img, int C, int H, int KT, int KH, int TPS, int KS) {
+  const int NC = H / TC_HC, n1 = KT * KH, n_per = n1 + KS;
+  const int CK = C / KH;                                   // input channels per W1 stage
+  const long long stage_elems = 128LL * CK;
   const long long total = (long long)NC * n_per * stage_elems;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx / stage_elems);
     const int e = (int)(idx % stage_elems);
     int is_w1, c, sub;
-    if (g < KT) { is_w1 = 1; c = 0; sub = g; }
+    if (g < n1) { is_w1 = 1; c = 0; sub = g; }
     else {
-      const int gp = g - KT, blk = gp / n_per, rem = gp % n_per;
+      const int gp = g - n1, blk = gp / n_per, rem = gp % n_per;
       if (blk < NC - 1) {
-        if (rem < KT) { is_w1 = 1; c = blk + 1; sub = rem; } else { is_w1 = 0; c = blk; sub = rem - KT; }
+        if (rem < n1) { is_w1 = 1; c = blk + 1; sub = rem; } else { is_w1 = 0; c = blk; sub = rem - n1; }
       } else { is_w1 = 0; c = NC - 1; sub = rem; }
     }
     float v = 0.f;
     if (is_w1) {
-      const int chunk = e / (64 * 8), n = (e / 8) % 64, cc = chunk * 8 + (e & 7);
+      const int k = sub / KH, hf = sub % KH;
+      const int chunk = e / (128 * 8), n = (e / 8) % 128, cc = hf * CK + chunk * 8 + (e & 7);
       const int row = n < TC_HC ? c * TC_HC + n : H + c * TC_HC + (n - TC_HC);
-      v = w1[((size_t)row * C + cc) * KT + sub];
+      v = w1[((size_t)row * C + cc) * KT + k];
     } else {
-      const int per_tap = 4 * C * 8;
+      const int per_tap = (TC_HC / 8) * C * 8;
       const int tl = e / per_tap, e2 = e % per_tap;
       const int chunk = e2 / (C * 8), n = (e2 / 8) % C, hh = chunk * 8 + (e2 & 7);
-      const int tap = 2 * sub + tl;
-      if (tap < KT) v = w2[((size_t)(c * TC_HC + hh) * C + n) * KT + (KT - 1 - tap)];
+      const int tap = TPS * sub + tl;
+      if (tl < TPS && tap < KT) v = w2[((size_t)(c * TC_HC + hh) * C + n) * KT + (KT - 1 - tap)];
     }
     img[idx] = __float2bfloat16_rn(v);
   }
@@ -99,8 +112,9 @@ __global__ void tc_pack_ffn_kernel(const float* __restrict__ w1, const float* __
 inline int tc_pack_ffn(const float* w1, const float* b1, const float* w2, const float* b2, char* img, int C, int H,
                        int K, cudaStream_t st) {
   (void)b1; (void)b2;
-  if (tc_ffn_image_bytes(C, H, K) == 0) return 0;  // shape not covered by the tcgen05 path
-  tc_pack_ffn_kernel<<<592, 256, 0, st>>>(w1, w2, (__nv_bfloat16*)img, C, H, K);
+  FfnTcGeom g;
+  if (!ffn_tc_geometry(C, H, K, 1, &g)) return 0;  // shape not covered by the tcgen05 path
+  tc_pack_ffn_kernel<<<592, 256, 0, st>>>(w1, w2, (__nv_bfloat16*)img, C, H, K, g.KH, g.TPS, g.KS);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -116,39 +130,53 @@ struct FfnTcParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(448, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom g) {
+// one tcgen05.mma from 32-bit descriptor halves (keeps the issue loop to a handful of integer adds)
+__device__ __forceinline__ void mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 ad, {%1, %2};\n\t"
+      "mov.b64 bd, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom g) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = g.C, H = g.H, KT = g.KT, NT = g.NT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS, NS = g.NS;
-  const int NA = NT + 1;
+  const int C = g.C, H = g.H, KT = g.KT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS, NS = g.NS;
+  const int KH = g.KH, TPS = g.TPS;
+  constexpr int NA = NT + 1;
   const uint32_t sbase = smem_u32(smem);
   float* tab_b1 = reinterpret_cast<float*>(smem + g.off_tab);
   float* tab_b2 = tab_b1 + 2 * H;
   float* tab_gamma = tab_b2 + C;
-  // barrier map (8 bytes each)
   const uint32_t bar0 = sbase + g.off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  // 0..7 w_full, 8..15 w_empty, 16..18 a_full, 19..21 a_empty, 22..25 d1_full[tile][buf], 26..29 d1_empty,
-  // 30..33 g_full, 34..37 g_empty, 38..39 d2_full, 40..41 d2_empty; 48: tmem base slot
-  const int W_FULL = 0, W_EMPTY = 8, A_FULL = 16, A_EMPTY = 19, D1_FULL = 22, D1_EMPTY = 26, G_FULL = 30, G_EMPTY = 34,
-            D2_FULL = 38, D2_EMPTY = 40;
+  // barrier map: 0..7 w_full, 8..15 w_empty, 16..18 a_full, 19..21 a_empty, 22..23 d1_full[tile], 24..25 d1_empty,
+  // 26..27 g_full, 28..29 g_empty, 30..31 d2_full, 32..33 d2_empty; slot 48: TMEM base address
+  const int W_FULL = 0, W_EMPTY = 8, A_FULL = 16, A_EMPTY = 19, D1_FULL = 22, D1_EMPTY = 24, G_FULL = 26, G_EMPTY = 28,
+            D2_FULL = 30, D2_EMPTY = 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bar + 8 * 48);
 
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) tab_b1[i] = p.b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) { tab_b2[i] = p.b2[i]; tab_gamma[i] = p.gamma[i]; }
   {  // hidden tiles: rows >= 128 are only ever read for discarded output rows; keep them finite
     uint32_t* gz = reinterpret_cast<uint32_t*>(smem + g.off_g);
-    for (uint32_t i = threadIdx.x; i < NT * 2 * g.g_buf_bytes / 4; i += blockDim.x) gz[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < NT * g.g_buf_bytes / 4; i += blockDim.x) gz[i] = 0u;
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(A_EMPTY + i), 1); }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(D1_FULL + i), 1); mbar_init(BAR(D1_EMPTY + i), 128);
       mbar_init(BAR(G_FULL + i), 128); mbar_init(BAR(G_EMPTY + i), 1);
+      mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 128);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -159,91 +187,101 @@ __global__ void __launch_bounds__(448, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom
   const uint32_t tmem = *tmem_slot;
   const int n_pairs = (p.n_tiles + NT - 1) / NT;
   const int n_iter = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int stages_per_iter = NC * (KT + KS);
-  const uint32_t d2_col0 = 4u * 2 * TC_HC;  // after the four D1 buffers
+  const int stages_per_iter = NC * (KT * KH + KS);
+  const uint32_t d2_col0 = 2u * 2 * TC_HC;  // after the two D1 tiles
 
   if (warp == 0) {
     // ===================== weight loader =====================
     if (lane == 0) {
-      long long n = 0;
-      for (int it = 0; it < n_iter; ++it)
-        for (int s = 0; s < stages_per_iter; ++s, ++n) {
-          const int slot = (int)(n % NS);
-          mbar_wait(BAR(W_EMPTY + slot), (uint32_t)(((n / NS) & 1) ^ 1));
+      uint32_t slot = 0, ph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const char* src = p.img;
+        for (int s = 0; s < stages_per_iter; ++s, src += g.stage_bytes) {
+          mbar_wait(BAR(W_EMPTY + slot), ph ^ 1);
           mbar_arrive_expect_tx(BAR(W_FULL + slot), g.stage_bytes);
-          bulk_g2s(sbase + g.off_w + slot * g.stage_bytes, p.img + (size_t)s * g.stage_bytes, g.stage_bytes,
-                   BAR(W_FULL + slot));
+          bulk_g2s(sbase + g.off_w + slot * g.stage_bytes, src, g.stage_bytes, BAR(W_FULL + slot));
+          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
         }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc1 = instr_desc(128, 2 * TC_HC), idesc2 = instr_desc(128, C);
-      const uint32_t lbo_a = AR * 16, lbo_b1 = 64 * 16, lbo_g = AR * 16, lbo_b2 = C * 16;
-      long long wn = 0;
-      auto wait_stage = [&]() -> uint32_t {
-        const int slot = (int)(wn % NS);
-        mbar_wait(BAR(W_FULL + slot), (uint32_t)((wn / NS) & 1));
-        tc_fence_after();
-        return sbase + g.off_w + slot * g.stage_bytes;
-      };
-      auto release_stage = [&]() { mma_commit(BAR(W_EMPTY + (int)(wn % NS))); ++wn; };
+      // descriptor words: lo = (addr >> 4) | (LBO/16 << 16); hi = SBO/16 | version(1) << 14
+      const uint32_t hi = (128u >> 4) | (1u << 14);
+      const uint32_t lo_a = (uint32_t)AR << 16;            // LBO = AR*16 for A and G tiles
+      const uint32_t lo_b1 = 128u << 16;                   // W1 stage: 128 rows -> LBO = 2048
+      const uint32_t lo_b2 = (uint32_t)C << 16;            // W2 stage: C rows   -> LBO = C*16
+      const uint32_t KK1 = C / KH / 16;                    // MMAs per W1 stage per tile
+      const uint32_t w16 = (sbase + g.off_w) >> 4, stage16 = g.stage_bytes >> 4;
+      const uint32_t g16 = (sbase + g.off_g) >> 4, gbuf16 = g.g_buf_bytes >> 4;
+      const uint32_t a16 = (sbase + g.off_a) >> 4, aslot16 = g.a_slot_bytes >> 4;
+      const uint32_t tap16 = (uint32_t)(TC_HC / 8) * C;    // one W2 tap = 8 chunks * C rows * 16 B
+      uint32_t wslot = 0, wph = 0;
+      uint32_t aslot[NT], aph[NT];
+#pragma unroll
+      _Pragma("unroll") for (int t = 0; t < NT; ++t) { aslot[t] = t; aph[t] = 0; }
+      uint32_t qpar = 0;                                   // parity of the running chunk counter
       for (int it = 0; it < n_iter; ++it) {
-        auto mma2 = [&](int cc) {
-          const long long qq = (long long)it * NC + cc;
-          const int gbuf = (int)(qq & 1);
-          for (int t = 0; t < NT; ++t) mbar_wait(BAR(G_FULL + t * 2 + gbuf), (uint32_t)((qq >> 1) & 1));
-          if (cc == 0) for (int t = 0; t < NT; ++t) mbar_wait(BAR(D2_EMPTY + t), (uint32_t)((it & 1) ^ 1));
+        auto mma2 = [&](int cc, uint32_t par) {
+          _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(G_FULL + t), par);
+          if (cc == 0) _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(D2_EMPTY + t), (uint32_t)((it & 1) ^ 1));
           tc_fence_after();
-          for (int sp = 0; sp < KS; ++sp) {
-            const uint32_t wb = wait_stage();
-            for (int t = 0; t < NT; ++t) {
-              const uint32_t gb = sbase + g.off_g + (t * 2 + gbuf) * g.g_buf_bytes;
-              for (int tl = 0; tl < 2; ++tl) {
-                const int tap = 2 * sp + tl;
+          for (int s = 0; s < KS; ++s) {
+            mbar_wait(BAR(W_FULL + wslot), wph);
+            tc_fence_after();
+            const uint32_t wb = w16 + wslot * stage16;
+            _Pragma("unroll") for (int t = 0; t < NT; ++t) {
+              const uint32_t gb = g16 + t * gbuf16;
+              const uint32_t dcol = tmem + d2_col0 + t * C;
+              for (int tl = 0; tl < TPS; ++tl) {
+                const int tap = s * TPS + tl;
                 if (tap >= KT) break;
-                for (int kk = 0; kk < TC_HC / 16; ++kk) {
-                  const uint64_t ad = smem_desc(gb + tap * 16 + kk * 2 * lbo_g, lbo_g, 128);
-                  const uint64_t bd = smem_desc(wb + tl * (4 * C * 16) + kk * 2 * lbo_b2, lbo_b2, 128);
-                  mma_ss(tmem + d2_col0 + t * C, ad, bd, idesc2, !(cc == 0 && tap == 0 && kk == 0));
-                }
+#pragma unroll
+                for (uint32_t kk = 0; kk < TC_HC / 16; ++kk)
+                  mma_lohi(dcol, (gb + tap + kk * 2 * AR) | lo_a, hi, (wb + tl * tap16 + kk * 2 * C) | lo_b2, hi, idesc2,
+                           (uint32_t)(cc | tap | (int)kk));
               }
             }
-            release_stage();
+            mma_commit(BAR(W_EMPTY + wslot));
+            if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
           }
-          for (int t = 0; t < NT; ++t) mma_commit(BAR(G_EMPTY + t * 2 + gbuf));
+          _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(G_EMPTY + t));
         };
         for (int c = 0; c < NC; ++c) {
-          const long long q = (long long)it * NC + c;
-          const int buf = (int)(q & 1);
-          for (int t = 0; t < NT; ++t) {
-            if (c == 0) {
-              const long long n = (long long)it * NT + t;
-              mbar_wait(BAR(A_FULL + (int)(n % NA)), (uint32_t)((n / NA) & 1));
-            }
-            mbar_wait(BAR(D1_EMPTY + t * 2 + buf), (uint32_t)(((q >> 1) & 1) ^ 1));
+          _Pragma("unroll") for (int t = 0; t < NT; ++t) {
+            if (c == 0) mbar_wait(BAR(A_FULL + aslot[t]), aph[t]);
+            mbar_wait(BAR(D1_EMPTY + t), qpar ^ 1);
           }
           tc_fence_after();
-          for (int k = 0; k < KT; ++k) {
-            const uint32_t wb = wait_stage();
-            for (int t = 0; t < NT; ++t) {
-              const long long n = (long long)it * NT + t;
-              const uint32_t ab = sbase + g.off_a + (uint32_t)(n % NA) * g.a_slot_bytes;
-              for (int kk = 0; kk < C / 16; ++kk) {
-                const uint64_t ad = smem_desc(ab + k * 16 + kk * 2 * lbo_a, lbo_a, 128);
-                const uint64_t bd = smem_desc(wb + kk * 2 * lbo_b1, lbo_b1, 128);
-                mma_ss(tmem + (t * 2 + buf) * (2 * TC_HC), ad, bd, idesc1, (k | kk) != 0);
+          for (int k = 0; k < KT; ++k)
+            for (int hf = 0; hf < KH; ++hf) {
+              mbar_wait(BAR(W_FULL + wslot), wph);
+              tc_fence_after();
+              const uint32_t wb = w16 + wslot * stage16;
+              _Pragma("unroll") for (int t = 0; t < NT; ++t) {
+                const uint32_t ab = a16 + aslot[t] * aslot16 + k + hf * KK1 * 2 * AR;
+                const uint32_t dcol = tmem + t * (2 * TC_HC);
+                for (uint32_t kk = 0; kk < KK1; ++kk)
+                  mma_lohi(dcol, (ab + kk * 2 * AR) | lo_a, hi, (wb + kk * 2 * 128) | lo_b1, hi, idesc1,
+                           (uint32_t)(k | hf | (int)kk));
               }
+              mma_commit(BAR(W_EMPTY + wslot));
+              if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
             }
-            release_stage();
-          }
-          for (int t = 0; t < NT; ++t) mma_commit(BAR(D1_FULL + t * 2 + buf));
+          _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(D1_FULL + t));
           if (c == NC - 1)
-            for (int t = 0; t < NT; ++t) mma_commit(BAR(A_EMPTY + (int)(((long long)it * NT + t) % NA)));
-          if (c > 0) mma2(c - 1);
+            _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(A_EMPTY + aslot[t]));
+          if (c > 0) mma2(c - 1, qpar ^ 1);
+          qpar ^= 1;
         }
-        mma2(NC - 1);
-        for (int t = 0; t < NT; ++t) mma_commit(BAR(D2_FULL + t));
+        mma2(NC - 1, qpar ^ 1);
+        _Pragma("unroll") for (int t = 0; t < NT; ++t) {
+          mma_commit(BAR(D2_FULL + t));
+          for (int a = 0; a < NT; ++a)   // advance this tile's A slot by NT positions in the NA ring
+            if (++aslot[t] == (uint32_t)NA) { aslot[t] = 0; aph[t] ^= 1; }
+        }
       }
     }
   } else if (warp < 6) {
@@ -251,11 +289,10 @@ __global__ void __launch_bounds__(448, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom
     const int tp = threadIdx.x - 64;  // 0..127
     const int G = g.G, D = C / G;
     const float rs = rsqrtf((float)D);
+    uint32_t slot = 0, ph = 0;
     for (int it = 0; it < n_iter; ++it)
-      for (int t = 0; t < NT; ++t) {
-        const long long n = (long long)it * NT + t;
-        const int slot = (int)(n % NA);
-        mbar_wait(BAR(A_EMPTY + slot), (uint32_t)(((n / NA) & 1) ^ 1));
+      _Pragma("unroll") for (int t = 0; t < NT; ++t) {
+        mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
         uint8_t* at = smem + g.off_a + (size_t)slot * g.a_slot_bytes;
         const long long tile = ((long long)blockIdx.x + (long long)it * gridDim.x) * NT + t;
         const long long r0 = tile * TS;
@@ -275,20 +312,22 @@ __global__ void __launch_bounds__(448, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom
               const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
               ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             }
-          const float denom = sqrtf(ss) * rs + p.eps;
+          const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
           for (int d = 0; d < D; d += 4) {
             uint2 pk = make_uint2(0u, 0u);
             const int c0 = grp * D + d;
             if (valid) {
               const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));  // L1 hit
-              pk.x = pack_bf16(v.x / denom * tab_gamma[c0], v.y / denom * tab_gamma[c0 + 1]);
-              pk.y = pack_bf16(v.z / denom * tab_gamma[c0 + 2], v.w / denom * tab_gamma[c0 + 3]);
+              const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+              pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
+              pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
             }
             *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * AR + row) * 16 + (c0 & 7) * 2) = pk;
           }
         }
         fence_proxy_async();
         mbar_arrive(BAR(A_FULL + slot));
+        if (++slot == (uint32_t)NA) { slot = 0; ph ^= 1; }
       }
   } else {
     // ===================== epilogue groups (one per tile slot) =====================
@@ -296,44 +335,47 @@ __global__ void __launch_bounds__(448, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;       // tile row
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* gt = smem + g.off_g + (size_t)t * g.g_buf_bytes;
+    uint32_t qpar = 0;
     for (int it = 0; it < n_iter; ++it) {
       for (int c = 0; c < NC; ++c) {
-        const long long q = (long long)it * NC + c;
-        const int buf = (int)(q & 1);
-        const uint32_t par = (uint32_t)((q >> 1) & 1);
-        mbar_wait(BAR(D1_FULL + t * 2 + buf), par);
+        mbar_wait(BAR(D1_FULL + t), qpar);
         tc_fence_after();
-        uint32_t rv[32], rg[32];
-        tmem_ld32(lane_addr + (t * 2 + buf) * (2 * TC_HC), rv);
-        tmem_ld32(lane_addr + (t * 2 + buf) * (2 * TC_HC) + TC_HC, rg);
-        tc_wait_ld();
-        tc_fence_before();
-        mbar_arrive(BAR(D1_EMPTY + t * 2 + buf));
-        mbar_wait(BAR(G_EMPTY + t * 2 + buf), par ^ 1);
-        uint8_t* gt = smem + g.off_g + (size_t)(t * 2 + buf) * g.g_buf_bytes;
+        uint32_t packed[TC_HC / 2];
         const float* bv = tab_b1 + c * TC_HC;
         const float* bg = tab_b1 + H + c * TC_HC;
 #pragma unroll
-        for (int ch = 0; ch < TC_HC / 8; ++ch) {
-          uint32_t o[4];
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(lane_addr + t * (2 * TC_HC) + half * 32, rv);
+          tmem_ld32(lane_addr + t * (2 * TC_HC) + TC_HC + half * 32, rg);
+          tc_wait_ld();
+          if (half == 1) {  // D1 fully read: hand it back to the MMA thread before the math
+            tc_fence_before();
+            mbar_arrive(BAR(D1_EMPTY + t));
+          }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int i = 0; i < 32; i += 2) {
             float hv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const int i = ch * 8 + e * 2 + u;
-              const float val = __uint_as_float(rv[i]) + bv[i];
-              const float gate = __uint_as_float(rg[i]) + bg[i];
+              const float val = __uint_as_float(rv[i + u]) + bv[half * 32 + i + u];
+              const float gate = __uint_as_float(rg[i + u]) + bg[half * 32 + i + u];
               hv[u] = val * gate * __frcp_rn(1.f + __expf(-gate));   // value * SiLU(gate), :648-649
             }
-            o[e] = pack_bf16(hv[0], hv[1]);
+            packed[half * 16 + (i >> 1)] = pack_bf16(hv[0], hv[1]);
           }
-          *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+        mbar_wait(BAR(G_EMPTY + t), qpar ^ 1);   // transposed-conv MMAs of the previous chunk are done with G
+#pragma unroll
+        for (int ch = 0; ch < TC_HC / 8; ++ch)
+          *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
+              make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
         fence_proxy_async();
-        mbar_arrive(BAR(G_FULL + t * 2 + buf));
+        mbar_arrive(BAR(G_FULL + t));
+        qpar ^= 1;
       }
-      // ---- final: transposed-conv accumulator + bias + residual -> x ----
+      // ---- final: transposed-conv accumulator + bias + residual -> y ----
       mbar_wait(BAR(D2_FULL + t), (uint32_t)(it & 1));
       tc_fence_after();
       const long long tile = ((long long)blockIdx.x + (long long)it * gridDim.x) * NT + t;
@@ -498,14 +540,16 @@ inline int tc_ffn(const tfl_plan* pl, const char* packed, int layer, int axis, i
   p.b1 = (const float*)(packed + f.b1raw); p.b2 = (const float*)(packed + f.b2);
   p.img = packed + f.tc;
   p.eps = c.eps;
-  static thread_local uint32_t smem_set = 0;
-  if (g.smem_bytes > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    smem_set = g.smem_bytes;
+  static thread_local uint32_t smem_set[2] = {0, 0};
+  if (g.smem_bytes > smem_set[g.NT - 1]) {
+    if (g.NT == 2) TFL_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    else TFL_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    smem_set[g.NT - 1] = g.smem_bytes;
   }
   const int n_pairs = (p.n_tiles + g.NT - 1) / g.NT;
   const int grid = n_pairs < pl->sm_count ? n_pairs : pl->sm_count;
-  ffn_tc_kernel<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
+  if (g.NT == 2) ffn_tc_kernel<2><<<grid, g.threads, g.smem_bytes, st>>>(p, g);
+  else ffn_tc_kernel<1><<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   TFL_LAUNCH_CHECK();
   return 0;
 }
