@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_attn.cuh"
 
 namespace tfl {
 
@@ -203,7 +204,7 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
 // ---- workspace ------------------------------------------------------------------------
 namespace tfl {
 struct Workspace {
-  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, tc, total;
+  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, tc, qkv_img, o_img, total;
   int gln_blocks;
 };
 static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int precision) {
@@ -227,6 +228,13 @@ static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int pr
   w.qkv = take(N * 3 * A * sizeof(float));
   w.o = take(N * A * sizeof(float));
   w.tc = take(tc_workspace_bytes(pl, B, Tf, F));
+  if (precision == TFL_PRECISION_BF16) {  // 128-row bf16 tile images of q|k|v and of the attention output
+    const size_t HDP = (size_t)(pl->head_dim + 15) / 16 * 16;
+    const size_t tiles_f = (size_t)B * Tf * ((F + 127) / 128), tiles_t = (size_t)B * F * ((Tf + 127) / 128);
+    const size_t tiles = tiles_f > tiles_t ? tiles_f : tiles_t;
+    w.o_img = take(tiles * 128 * c.n_heads * HDP * 2);
+    w.qkv_img = take(3 * tiles * 128 * c.n_heads * HDP * 2);
+  }
   w.total = off;
   return w;
 }
@@ -309,6 +317,50 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
   return gemm_launch(g2, EpiResidual{x, xmap}, st);
 }
 
+// bf16 attention sub-block: x += Wo . softmax(rope(q) rope(k)^T) v, with the tcgen05 attention kernel.
+// (interim: the two projections still run on the fp32 tap-GEMM; q/k/v and o cross HBM as bf16 tile images)
+static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
+                     const Workspace& ws, char* wsp, cudaStream_t st) {
+  const tfl_config& c = pl->cfg;
+  const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
+  const int C = c.emb_dim, A = c.attention_dim, hd = pl->head_dim, heads = c.n_heads;
+  TFL_CHECK(hd % 8 == 0 && hd <= 32, "bf16 tcgen05 attention needs head_dim in {8, 16, 24, 32} (got %d); use precision fp32", hd);
+  const int HDP = (hd + 15) / 16 * 16;
+  const int L = axis == TFL_AXIS_FREQ ? d.F : d.Tf;
+  const int nseq = axis == TFL_AXIS_FREQ ? d.B * d.Tf : d.B * d.F;
+  const int NTL = (L + 127) / 128;
+  const long long rows = (long long)d.B * d.Tf * d.F;
+  float* xn = (float*)(wsp + ws.xn);
+  __nv_bfloat16* qkv = (__nv_bfloat16*)(wsp + ws.qkv_img);
+  __nv_bfloat16* oimg = (__nv_bfloat16*)(wsp + ws.o_img);
+  float* o = (float*)(wsp + ws.o);
+  const size_t qkv_bytes = (size_t)3 * nseq * heads * NTL * HDP * 128 * 2;
+  if (norm_launch(x, xn, rows, C, c.num_groups, (const float*)(packed + p.attn_gamma), c.eps, pl->sm_count, st)) return -1;
+  TFL_CUDA(cudaMemsetAsync(qkv, 0, qkv_bytes, st));
+  const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
+  TapGemm g1{xn, xmap, L, L, 0, 1, C, (const float*)(packed + p.wqkv), nullptr, 3 * A, (long long)nseq * L};
+  EpiQkvImg e1{qkv, A, hd, heads, L, nseq, NTL, HDP, c.rope ? (const float*)(packed + p.rope) : nullptr,
+               1.4426950408889634f / sqrtf((float)hd)};
+  if (gemm_launch(g1, e1, st)) return -1;
+  AttnTcParams ap;
+  ap.qkv = qkv; ap.o = oimg; ap.nseq = nseq; ap.heads = heads; ap.L = L; ap.NTL = NTL; ap.HDP = HDP;
+  ap.NP = (NTL + 1) / 2; ap.n_items = nseq * heads * ap.NP;
+  const uint32_t smem = attn_tc_smem(HDP);
+  static thread_local uint32_t smem_set = 0;
+  if (smem > smem_set) {
+    TFL_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
+  attn_tc_kernel<<<grid, 320, smem, st>>>(ap);
+  TFL_LAUNCH_CHECK();
+  oimg_to_f32_kernel<<<pl->sm_count * 8, 256, 0, st>>>(oimg, o, nseq, L, NTL, heads, hd, HDP);
+  TFL_LAUNCH_CHECK();
+  TapGemm g2{o, make_dense_map((long long)L * A, A), L, L, 0, 1, A, (const float*)(packed + p.wo), nullptr, C,
+             (long long)nseq * L};
+  return gemm_launch(g2, EpiResidual{x, xmap}, st);
+}
+
 // LocoformerBlock.forward, models/mss_tflocoformer.py:430-464.  fp32: in place on *cur.  bf16: every fused
 // FFN kernel reads *cur and writes *alt (tile halos forbid in-place), after which the two swap.
 static int path_forward(const tfl_plan* pl, const char* packed, int layer, int axis, float** cur, float** alt, Dims d,
@@ -322,7 +374,9 @@ static int path_forward(const tfl_plan* pl, const char* packed, int layer, int a
     return ffn_f32(pl, packed, layer, axis, j, *cur, d, ws, wsp, st);
   };
   if (pl->cfg.macaron && ffn(1)) return -1;
-  if (attn_f32(pl, packed, layer, axis, *cur, d, ws, wsp, st)) return -1;
+  if (precision == TFL_PRECISION_BF16) {
+    if (attn_bf16(pl, packed, layer, axis, *cur, d, ws, wsp, st)) return -1;
+  } else if (attn_f32(pl, packed, layer, axis, *cur, d, ws, wsp, st)) return -1;
   return ffn(0);
 }
 
@@ -430,6 +484,8 @@ int tfl_rope_attn(const tfl_plan* pl, const void* packed, int layer, int axis, f
   TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer/axis");
   const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
   TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  if (precision == TFL_PRECISION_BF16)
+    return attn_bf16(pl, (const char*)packed, layer, axis, x, Dims{B, Tf, F}, ws, (char*)workspace, (cudaStream_t)stream);
   return attn_f32(pl, (const char*)packed, layer, axis, x, Dims{B, Tf, F}, ws, (char*)workspace, (cudaStream_t)stream);
 }
 

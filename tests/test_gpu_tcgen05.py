@@ -114,3 +114,35 @@ def test_real_width_one_layer_bf16(pkg, name, cfg, n_samples):
         got = model(mix.cuda())
     for k in want:
         assert oracle.si_sdr_db(got[k].cpu(), want[k]) >= 40.0, (name, k)
+
+
+@pytest.mark.parametrize("name,cfg,shape", [("golden32", None, None), ("D", VARIANT_D, (1, 5, 300)),
+                                            ("Y", VARIANT_Y, (2, 7, 131)), ("D_long", VARIANT_D, (1, 3, 1025)),
+                                            ("D_time", VARIANT_D, (1, 259, 6))])
+def test_attention_tc_vs_oracle(pkg, name, cfg, shape):
+    """tcgen05 attention (S = QK^T and P.V on the tensor core, exp2 softmax) on both axes."""
+    if cfg is None:
+        cfg, sd, arr = load_golden("mss_hop2_macaron")
+        model = pkg.TFLocoformerMSS(**cfg)
+        model.load_state_dict(sd)
+        xin = arr["stage/conv:out"].permute(0, 2, 3, 1).contiguous()
+    else:
+        model = _random_model(pkg, cfg)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        g = torch.Generator().manual_seed(3)
+        xin = torch.randn(*shape, cfg["emb_dim"], generator=g)
+    model = model.cuda().eval()
+    eng = model._ready()
+    for axis, path in ((0, "freq_path"), (1, "frame_path")):
+        p = f"blocks.0.{path}"
+        xa = xin if axis == 0 else xin.transpose(1, 2).contiguous()
+        b, s1, s2, c = xa.shape
+        xn = oracle.rms_group_norm(xa, sd[f"{p}.attn_norm.gamma"], cfg["num_groups"], cfg["eps"])
+        y = oracle.attention(xn.reshape(b * s1, s2, c), sd[f"{p}.attn.qkv.weight"],
+                             sd[f"{p}.attn.aggregate_heads.0.weight"], cfg["n_heads"],
+                             sd.get(f"{p}.attn.rope.freqs")).reshape(xa.shape)
+        branch = y if axis == 0 else y.transpose(1, 2)
+        got = eng.attn_(0, axis, xin.cuda().clone(), 1).cpu() - xin
+        sdr = oracle.si_sdr_db(got, branch)
+        assert sdr > 35.0, (name, axis, sdr)
+        assert float((got - branch).abs().max()) < 0.06 * float(branch.abs().max()) + 1e-3, (name, axis)
