@@ -244,43 +244,310 @@ inline uint32_t attn_tc_smem(int HDP) {
   return (uint32_t)(2 + ATT_STAGES * 2) * HDP * 128 * 2 + 2 * 128 * 128 * 2 + 512;
 }
 
-// ---- interim glue while the projections still run on the fp32 tap-GEMM ------------------------------
-struct EpiQkvImg {  // tap-GEMM epilogue: RoPE + softmax pre-scale, bf16 tile images (layout above)
-  __nv_bfloat16* img; int A, hd, heads, L, nseq, NTL, HDP; const float* freqs; float qscale;
-  __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      const int n = n0 + i;
-      if (n >= N) break;
-      const int which = n / A, rem = n - which * A, head = rem / hd, d = rem - head * hd;
-      float a = v[i], b = v[i + 1];
-      if (freqs != nullptr && which < 2) {
-        const float ang = (float)j * __ldg(&freqs[d >> 1]);
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        const float ra = a * cs - b * sn, rb = b * cs + a * sn;
-        a = ra; b = rb;
-      }
-      if (which == 0) { a *= qscale; b *= qscale; }
-      const size_t tile = (((size_t)which * nseq + s) * heads + head) * NTL + (j >> 7);
-      __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
-      *reinterpret_cast<__nv_bfloat162*>(img + tile * ((size_t)HDP * 128) + ((size_t)(d >> 3) * 128 + (j & 127)) * 8 + (d & 7)) = pk;
-    }
-  }
+// --------------------------------------------------------------------------------------------
+// qkv_tc_kernel: RMSGroupNorm -> q|k|v projection (tcgen05) -> RoPE + softmax pre-scale -> bf16 tile images
+// (models/mss_tflocoformer.py:452-453, :542-559).  M tiles are sequence-aligned (seq s, tile jt) so each CTA
+// writes complete 128-row images (rows >= L come out as exact zeros because their A rows are zero).
+//   warp 0: weight image (bulk copy, once)   warp 1: MMA thread   warps 2-5: norm producers
+//   warps 6-13: two epilogue groups, each owning half of the columns of every part
+// TMEM: three part accumulators (q, k, v) of NPART = heads * HDP columns used as a ring across tiles.
+// --------------------------------------------------------------------------------------------
+struct QkvTcParams {
+  const float* x; SeqMap map; const float* gamma; float eps;
+  const char* wimg;                 // [3 parts][C/8 chunks][NPART rows][8] bf16
+  const float2* rope;               // [L][HDP/2] (cos, sin) or nullptr ("nope")
+  __nv_bfloat16* qkv;               // tile images
+  int C, G, L, NTL, nseq, heads, hd, HDP, NPART;
+  int n_tiles;
+  float qscale;
 };
 
-__global__ void oimg_to_f32_kernel(const __nv_bfloat16* __restrict__ img, float* __restrict__ o, int nseq, int L,
-                                   int NTL, int heads, int hd, int HDP) {
-  const int A = heads * hd;
-  const long long total = (long long)nseq * L * A;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int a = (int)(i % A);
-    const long long row = i / A;
-    const int j = (int)(row % L), s = (int)(row / L);
-    const int h = a / hd, d = a - h * hd;
-    const size_t chunk = (size_t)h * (HDP / 8) + (d >> 3);
-    o[i] = __bfloat162float(img[(((size_t)s * NTL + (j >> 7)) * (heads * (HDP / 8)) + chunk) * 1024 + (size_t)(j & 127) * 8 + (d & 7)]);
+__global__ void rope_table_kernel(float2* __restrict__ tab, const float* __restrict__ freqs, int L, int half, int half_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * half_pad) return;
+  const int j = i / half_pad, f = i - j * half_pad;
+  float sn = 0.f, cs = 1.f;
+  if (f < half) sincosf((float)j * freqs[f], &sn, &cs);   // same fp32 product as the reference's einsum
+  tab[i] = make_float2(cs, sn);
+}
+
+__global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* __restrict__ wo,
+                                   __nv_bfloat16* __restrict__ qimg, __nv_bfloat16* __restrict__ oimg, int C, int A,
+                                   int heads, int hd, int HDP) {
+  const int NPART = heads * HDP;
+  const int n_q = 3 * C * NPART, n_o = NPART * C;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_q + n_o; idx += gridDim.x * blockDim.x) {
+    if (idx < n_q) {   // part image: [C/8][NPART][8]; row n = head*HDP + d  <-  wqkv[part*A + head*hd + d][c]
+      const int part = idx / (C * NPART), e = idx % (C * NPART);
+      const int chunk = e / (NPART * 8), n = (e / 8) % NPART, c = chunk * 8 + (e & 7);
+      const int head = n / HDP, d = n % HDP;
+      qimg[idx] = __float2bfloat16_rn(d < hd ? wqkv[((size_t)part * A + head * hd + d) * C + c] : 0.f);
+    } else {           // wo image: [NPART/8][C rows][8]; row n = out channel, k = head*HDP + d  <-  wo[n][head*hd + d]
+      const int e = idx - n_q;
+      const int chunk = e / (C * 8), n = (e / 8) % C, k = chunk * 8 + (e & 7);
+      const int head = k / HDP, d = k % HDP;
+      oimg[e] = __float2bfloat16_rn(d < hd ? wo[(size_t)n * A + head * hd + d] : 0.f);
+    }
   }
+}
+
+__global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.C, NPART = p.NPART, HDP = p.HDP, NTL = p.NTL;
+  const uint32_t part_bytes = (uint32_t)C * NPART * 2, a_bytes = (uint32_t)C * 128 * 2;
+  const uint32_t off_w = 0, off_a = 3 * part_bytes, off_tab = off_a + 3 * a_bytes, off_bar = off_tab + C * 4;
+  const uint32_t sbase = smem_u32(smem);
+  auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
+  const int W_FULL = 0, A_FULL = 1, A_EMPTY = 4, D_FULL = 7, D_EMPTY = 10;   // A: 3 slots, D: 3 parts
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 16);
+  float* tab_gamma = reinterpret_cast<float*>(smem + off_tab);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) tab_gamma[i] = p.gamma[i];
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(W_FULL), 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(A_EMPTY + i), 1);
+      mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_iter = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(BAR(W_FULL), 3 * part_bytes);
+      for (int i = 0; i < 3; ++i) bulk_g2s(sbase + off_w + i * part_bytes, p.wimg + (size_t)i * part_bytes, part_bytes, BAR(W_FULL));
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(128, NPART);
+      const uint32_t hi = (128u >> 4) | (1u << 14);
+      const uint32_t lo_a = 128u << 16, lo_b = (uint32_t)NPART << 16;
+      const uint32_t a16 = (sbase + off_a) >> 4, w16 = (sbase + off_w) >> 4, as16 = a_bytes >> 4, ps16 = part_bytes >> 4;
+      mbar_wait(BAR(W_FULL), 0);
+      uint32_t slot = 0, aph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        mbar_wait(BAR(A_FULL + slot), aph);
+        for (int part = 0; part < 3; ++part) {
+          mbar_wait(BAR(D_EMPTY + part), (uint32_t)((it & 1) ^ 1));
+          tc_fence_after();
+          for (int kk = 0; kk < C / 16; ++kk)
+            mma_lohi(tmem + part * NPART, (a16 + slot * as16 + kk * 2 * 128) | lo_a, hi,
+                     (w16 + part * ps16 + kk * 2 * NPART) | lo_b, hi, idesc, (uint32_t)kk);
+          mma_commit(BAR(D_FULL + part));
+        }
+        mma_commit(BAR(A_EMPTY + slot));
+        if (++slot == 3) { slot = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    const int tp = threadIdx.x - 64;
+    const int G = p.G, D = C / G;
+    const float rs = rsqrtf((float)D);
+    uint32_t slot = 0, ph = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
+      uint8_t* at = smem + off_a + (size_t)slot * a_bytes;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = tile / NTL, jt = tile - s * NTL;
+      const long long base = p.map.base(s);
+      for (int item = tp; item < 128 * G; item += 128) {
+        const int row = item / G, grp = item - row * G;
+        const int j = jt * 128 + row;
+        const bool valid = j < p.L;
+        const float* src = p.x + base + (long long)j * p.map.pos_stride + grp * D;
+        float ss = 0.f;
+        if (valid)
+          for (int d = 0; d < D; d += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          }
+        const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+        for (int d = 0; d < D; d += 4) {
+          uint2 pk = make_uint2(0u, 0u);
+          const int c0 = grp * D + d;
+          if (valid) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+            const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+            pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
+            pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
+          }
+          *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(BAR(A_FULL + slot));
+      if (++slot == 3) { slot = 0; ph ^= 1; }
+    }
+  } else {
+    const int e = (warp - 6) >> 2;             // column half owned by this group
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int col_lo = e * (NPART / 2), col_hi = col_lo + NPART / 2;
+    const int halfp = HDP / 2;
+    const size_t tile_elems = (size_t)HDP * 128;
+    for (int it = 0; it < n_iter; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = tile / NTL, jt = tile - s * NTL;
+      const int j = min(jt * 128 + m, p.L - 1);
+      const float2* rt = p.rope != nullptr ? p.rope + (size_t)j * halfp : nullptr;
+      for (int part = 0; part < 3; ++part) {
+        mbar_wait(BAR(D_FULL + part), (uint32_t)(it & 1));
+        tc_fence_after();
+        for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + part * NPART + c0, r);
+          tc_wait_ld();
+          const int head = c0 / HDP, d0 = c0 - head * HDP;
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
+            if (part < 2 && rt != nullptr) {
+              const float2 cs = __ldg(&rt[(d0 + i) >> 1]);
+              const float ra = a * cs.x - b * cs.y, rb = b * cs.x + a * cs.y;
+              a = ra; b = rb;
+            }
+            if (part == 0) { a *= p.qscale; b *= p.qscale; }
+            w[i >> 1] = pack_bf16(a, b);
+          }
+          __nv_bfloat16* dst = p.qkv + ((((size_t)part * p.nseq + s) * p.heads + head) * NTL + jt) * tile_elems +
+                               ((size_t)(d0 >> 3) * 128 + m) * 8;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(dst + 1024) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(D_EMPTY + part));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// --------------------------------------------------------------------------------------------
+// proj_tc_kernel: x += o . Wo^T (head merge + residual, :536-540, :456).  A tiles are the attention kernel's o
+// images (one bulk copy each), Wo stays resident in smem, accumulators double-buffered in TMEM.
+//   warp 0: loader   warp 1: MMA thread   warps 2-9: two epilogue groups alternating tiles
+// --------------------------------------------------------------------------------------------
+struct ProjTcParams {
+  const __nv_bfloat16* oimg; const char* wimg; float* x; SeqMap map;
+  int C, AP, L, NTL, n_tiles;
+};
+constexpr int PROJ_STAGES = 4;
+
+__global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.C, AP = p.AP, NTL = p.NTL;
+  const uint32_t w_bytes = (uint32_t)AP * C * 2, a_bytes = (uint32_t)AP * 128 * 2;
+  const uint32_t off_w = 0, off_a = w_bytes, off_bar = off_a + PROJ_STAGES * a_bytes;
+  const uint32_t sbase = smem_u32(smem);
+  auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
+  const int W_FULL = 0, A_FULL = 1, A_EMPTY = 5, D_FULL = 9, D_EMPTY = 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 16);
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(W_FULL), 1);
+    for (int i = 0; i < PROJ_STAGES; ++i) { mbar_init(BAR(A_FULL + i), 1); mbar_init(BAR(A_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_iter = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(BAR(W_FULL), w_bytes);
+      bulk_g2s(sbase + off_w, p.wimg, w_bytes, BAR(W_FULL));
+      uint32_t slot = 0, ph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
+        mbar_arrive_expect_tx(BAR(A_FULL + slot), a_bytes);
+        bulk_g2s(sbase + off_a + slot * a_bytes, p.oimg + (size_t)tile * AP * 128, a_bytes, BAR(A_FULL + slot));
+        if (++slot == PROJ_STAGES) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(128, C);
+      const uint32_t hi = (128u >> 4) | (1u << 14);
+      const uint32_t lo_a = 128u << 16, lo_b = (uint32_t)C << 16;
+      const uint32_t a16 = (sbase + off_a) >> 4, w16 = (sbase + off_w) >> 4, as16 = a_bytes >> 4;
+      mbar_wait(BAR(W_FULL), 0);
+      uint32_t slot = 0, ph = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        mbar_wait(BAR(A_FULL + slot), ph);
+        mbar_wait(BAR(D_EMPTY + buf), (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int kk = 0; kk < AP / 16; ++kk)
+          mma_lohi(tmem + buf * C, (a16 + slot * as16 + kk * 2 * 128) | lo_a, hi, (w16 + kk * 2 * C) | lo_b, hi, idesc,
+                   (uint32_t)kk);
+        mma_commit(BAR(D_FULL + buf));
+        mma_commit(BAR(A_EMPTY + slot));
+        if (++slot == PROJ_STAGES) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int e = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int it = e; it < n_iter; it += 2) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = tile / NTL, jt = tile - s * NTL;
+      const int j = jt * 128 + m;
+      mbar_wait(BAR(D_FULL + e), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float* dst = j < p.L ? p.x + p.map.base(s) + (long long)j * p.map.pos_stride : nullptr;
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + e * C + c0, r);
+        tc_wait_ld();
+        if (dst != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 xv = *reinterpret_cast<const float4*>(dst + c0 + i);
+            xv.x += __uint_as_float(r[i]); xv.y += __uint_as_float(r[i + 1]);
+            xv.z += __uint_as_float(r[i + 2]); xv.w += __uint_as_float(r[i + 3]);
+            *reinterpret_cast<float4*>(dst + c0 + i) = xv;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(D_EMPTY + e));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+inline bool attn_tc_supported(int C, int heads, int hd) {
+  if (hd % 8 != 0 || hd > 32 || C % 16 != 0 || C > 256) return false;
+  const int HDP = (hd + 15) / 16 * 16, NPART = heads * HDP;
+  if (NPART % 32 != 0 || NPART > 128) return false;
+  return (size_t)3 * C * NPART * 2 + (size_t)3 * C * 256 + C * 4 + 256 <= (size_t)232448;
+}
+inline size_t tc_qkv_image_bytes(int C, int heads, int hd) {
+  return attn_tc_supported(C, heads, hd) ? (size_t)3 * C * heads * ((hd + 15) / 16 * 16) * 2 : 0;
+}
+inline size_t tc_wo_image_bytes(int C, int heads, int hd) {
+  return attn_tc_supported(C, heads, hd) ? (size_t)C * heads * ((hd + 15) / 16 * 16) * 2 : 0;
 }
 
 }  // namespace tfl

@@ -85,7 +85,8 @@ static void build_layout(tfl_plan* pl) {
     p.rope = take(pl->head_dim / 2 + 1);
     p.wqkv = take((size_t)C * 3 * A);
     p.wo = take((size_t)A * C);
-    p.tc_qkv = p.tc_wo = 0;
+    p.tc_qkv = take(tc_qkv_image_bytes(C, c.n_heads, pl->head_dim) / sizeof(float));
+    p.tc_wo = take(tc_wo_image_bytes(C, c.n_heads, pl->head_dim) / sizeof(float));
   }
   L.total = off;
 }
@@ -185,8 +186,14 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
       }
       copy(w[i++], p.attn_gamma, C);
       if (c.rope) copy(w[i++], p.rope, pl->head_dim / 2);
-      permute(w[i++], dst(p.wqkv), 1, 1, C, 3 * A, 0, 0, 1, C, 0, -1, st);  // [3A, C] -> [C][3A]
-      permute(w[i++], dst(p.wo), 1, 1, A, C, 0, 0, 1, A, 0, -1, st);        // [C, A] -> [A][C]
+      const float* wqkv_raw = w[i++];
+      const float* wo_raw = w[i++];
+      permute(wqkv_raw, dst(p.wqkv), 1, 1, C, 3 * A, 0, 0, 1, C, 0, -1, st);  // [3A, C] -> [C][3A]
+      permute(wo_raw, dst(p.wo), 1, 1, A, C, 0, 0, 1, A, 0, -1, st);          // [C, A] -> [A][C]
+      if (attn_tc_supported(C, c.n_heads, pl->head_dim))
+        tc_pack_qkv_kernel<<<296, 256, 0, st>>>(wqkv_raw, wo_raw, (__nv_bfloat16*)(base + p.tc_qkv),
+                                                (__nv_bfloat16*)(base + p.tc_wo), C, A, c.n_heads, pl->head_dim,
+                                                (pl->head_dim + 15) / 16 * 16);
     }
   if (c.enc_in_ch > 0) {
     // deconv.weight [C, 2S, 3, 3] -> [9][C][8]
@@ -204,7 +211,7 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
 // ---- workspace ------------------------------------------------------------------------
 namespace tfl {
 struct Workspace {
-  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, tc, qkv_img, o_img, total;
+  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, tc, qkv_img, o_img, rope, total;
   int gln_blocks;
 };
 static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int precision) {
@@ -234,6 +241,7 @@ static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int pr
     const size_t tiles = tiles_f > tiles_t ? tiles_f : tiles_t;
     w.o_img = take(tiles * 128 * c.n_heads * HDP * 2);
     w.qkv_img = take(3 * tiles * 128 * c.n_heads * HDP * 2);
+    w.rope = take((size_t)(F > Tf ? F : Tf) * (HDP / 2) * sizeof(float2));
   }
   w.total = off;
   return w;
@@ -317,48 +325,73 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
   return gemm_launch(g2, EpiResidual{x, xmap}, st);
 }
 
-// bf16 attention sub-block: x += Wo . softmax(rope(q) rope(k)^T) v, with the tcgen05 attention kernel.
-// (interim: the two projections still run on the fp32 tap-GEMM; q/k/v and o cross HBM as bf16 tile images)
+// bf16 attention sub-block (models/mss_tflocoformer.py:452-456): three tcgen05 kernels,
+//   qkv_tc   RMSGroupNorm -> q|k|v projection -> RoPE -> bf16 tile images
+//   attn_tc  softmax(q k^T) v per (sequence, head)
+//   proj_tc  head merge projection + residual, in place on x
 static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
                      const Workspace& ws, char* wsp, cudaStream_t st) {
   const tfl_config& c = pl->cfg;
   const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
-  const int C = c.emb_dim, A = c.attention_dim, hd = pl->head_dim, heads = c.n_heads;
-  TFL_CHECK(hd % 8 == 0 && hd <= 32, "bf16 tcgen05 attention needs head_dim in {8, 16, 24, 32} (got %d); use precision fp32", hd);
-  const int HDP = (hd + 15) / 16 * 16;
+  const int C = c.emb_dim, hd = pl->head_dim, heads = c.n_heads;
+  TFL_CHECK(attn_tc_supported(C, heads, hd),
+            "bf16 tcgen05 attention needs head_dim in {8,16,24,32}, emb_dim %% 16 == 0 and n_heads * head_dim(padded to 16) "
+            "in {32,64,96,128} (got emb_dim %d, n_heads %d, head_dim %d); use precision fp32", C, heads, hd);
+  const int HDP = (hd + 15) / 16 * 16, NPART = heads * HDP;
   const int L = axis == TFL_AXIS_FREQ ? d.F : d.Tf;
   const int nseq = axis == TFL_AXIS_FREQ ? d.B * d.Tf : d.B * d.F;
   const int NTL = (L + 127) / 128;
-  const long long rows = (long long)d.B * d.Tf * d.F;
-  float* xn = (float*)(wsp + ws.xn);
   __nv_bfloat16* qkv = (__nv_bfloat16*)(wsp + ws.qkv_img);
   __nv_bfloat16* oimg = (__nv_bfloat16*)(wsp + ws.o_img);
-  float* o = (float*)(wsp + ws.o);
-  const size_t qkv_bytes = (size_t)3 * nseq * heads * NTL * HDP * 128 * 2;
-  if (norm_launch(x, xn, rows, C, c.num_groups, (const float*)(packed + p.attn_gamma), c.eps, pl->sm_count, st)) return -1;
-  TFL_CUDA(cudaMemsetAsync(qkv, 0, qkv_bytes, st));
+  float2* rope = (float2*)(wsp + ws.rope);
   const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
-  TapGemm g1{xn, xmap, L, L, 0, 1, C, (const float*)(packed + p.wqkv), nullptr, 3 * A, (long long)nseq * L};
-  EpiQkvImg e1{qkv, A, hd, heads, L, nseq, NTL, HDP, c.rope ? (const float*)(packed + p.rope) : nullptr,
-               1.4426950408889634f / sqrtf((float)hd)};
-  if (gemm_launch(g1, e1, st)) return -1;
-  AttnTcParams ap;
-  ap.qkv = qkv; ap.o = oimg; ap.nseq = nseq; ap.heads = heads; ap.L = L; ap.NTL = NTL; ap.HDP = HDP;
-  ap.NP = (NTL + 1) / 2; ap.n_items = nseq * heads * ap.NP;
-  const uint32_t smem = attn_tc_smem(HDP);
-  static thread_local uint32_t smem_set = 0;
-  if (smem > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  static thread_local uint32_t smem_set[3] = {0, 0, 0};
+  if (c.rope) {
+    rope_table_kernel<<<(L * (HDP / 2) + 255) / 256, 256, 0, st>>>(rope, (const float*)(packed + p.rope), L, hd / 2, HDP / 2);
+    TFL_LAUNCH_CHECK();
   }
-  const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
-  attn_tc_kernel<<<grid, 320, smem, st>>>(ap);
-  TFL_LAUNCH_CHECK();
-  oimg_to_f32_kernel<<<pl->sm_count * 8, 256, 0, st>>>(oimg, o, nseq, L, NTL, heads, hd, HDP);
-  TFL_LAUNCH_CHECK();
-  TapGemm g2{o, make_dense_map((long long)L * A, A), L, L, 0, 1, A, (const float*)(packed + p.wo), nullptr, C,
-             (long long)nseq * L};
-  return gemm_launch(g2, EpiResidual{x, xmap}, st);
+  {
+    QkvTcParams q;
+    q.x = x; q.map = xmap; q.gamma = (const float*)(packed + p.attn_gamma); q.eps = c.eps;
+    q.wimg = packed + p.tc_qkv; q.rope = c.rope ? rope : nullptr; q.qkv = qkv;
+    q.C = C; q.G = c.num_groups; q.L = L; q.NTL = NTL; q.nseq = nseq; q.heads = heads; q.hd = hd; q.HDP = HDP;
+    q.NPART = NPART; q.n_tiles = nseq * NTL; q.qscale = 1.4426950408889634f / sqrtf((float)hd);
+    const uint32_t smem = 3u * C * NPART * 2 + 3u * C * 256 + C * 4 + 256;
+    if (smem > smem_set[0]) {
+      TFL_CUDA(cudaFuncSetAttribute(qkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[0] = smem;
+    }
+    const int grid = q.n_tiles < pl->sm_count ? q.n_tiles : pl->sm_count;
+    qkv_tc_kernel<<<grid, 448, smem, st>>>(q);
+    TFL_LAUNCH_CHECK();
+  }
+  {
+    AttnTcParams ap;
+    ap.qkv = qkv; ap.o = oimg; ap.nseq = nseq; ap.heads = heads; ap.L = L; ap.NTL = NTL; ap.HDP = HDP;
+    ap.NP = (NTL + 1) / 2; ap.n_items = nseq * heads * ap.NP;
+    const uint32_t smem = attn_tc_smem(HDP);
+    if (smem > smem_set[1]) {
+      TFL_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[1] = smem;
+    }
+    const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
+    attn_tc_kernel<<<grid, 320, smem, st>>>(ap);
+    TFL_LAUNCH_CHECK();
+  }
+  {
+    ProjTcParams pp;
+    pp.oimg = oimg; pp.wimg = packed + p.tc_wo; pp.x = x; pp.map = xmap;
+    pp.C = C; pp.AP = NPART; pp.L = L; pp.NTL = NTL; pp.n_tiles = nseq * NTL;
+    const uint32_t smem = (uint32_t)NPART * C * 2 + PROJ_STAGES * (uint32_t)NPART * 256 + 256;
+    if (smem > smem_set[2]) {
+      TFL_CUDA(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[2] = smem;
+    }
+    const int grid = pp.n_tiles < pl->sm_count ? pp.n_tiles : pl->sm_count;
+    proj_tc_kernel<<<grid, 320, smem, st>>>(pp);
+    TFL_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 // LocoformerBlock.forward, models/mss_tflocoformer.py:430-464.  fp32: in place on *cur.  bf16: every fused
