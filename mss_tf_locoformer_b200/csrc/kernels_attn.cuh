@@ -40,24 +40,25 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HDP = p.HDP, NTL = p.NTL;
-  const uint32_t tile_bytes = (uint32_t)HDP * 128 * 2;          // one Q / K / V tile
-  const uint32_t p_bytes = 128u * 128 * 2;                       // one P tile
-  const uint32_t off_q = 0, off_kv = 2 * tile_bytes, off_p = off_kv + ATT_STAGES * 2 * tile_bytes;
-  const uint32_t off_bar = off_p + 2 * p_bytes;
+  const int NU = (p.L + 63) / 64;                                 // 64-key units per sequence
+  const uint32_t tile_bytes = (uint32_t)HDP * 128 * 2;          // one Q / K / V tile (128 rows)
+  const uint32_t p_bytes = 128u * 64 * 2;                        // one P half-tile (128 queries x 64 keys)
+  const uint32_t off_q = 0, off_kv = 4 * tile_bytes, off_p = off_kv + ATT_STAGES * 2 * tile_bytes;
+  const uint32_t off_bar = off_p + 4 * p_bytes;
   const uint32_t sbase = smem_u32(smem);
   auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
-  // 0..3 kv_full, 4..7 kv_empty, 8..9 q_full[g], 10..11 q_empty[g], 12..13 s_full[g], 14..15 s_empty[g],
-  // 16..17 p_full[g], 18..19 p_empty[g], 20..23 o_full[g][buf], 24..27 o_empty[g][buf]; slot 32: TMEM base
-  const int KV_FULL = 0, KV_EMPTY = 4, Q_FULL = 8, Q_EMPTY = 10, S_FULL = 12, S_EMPTY = 14, P_FULL = 16, P_EMPTY = 18,
-            O_FULL = 20, O_EMPTY = 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 32);
+  // 0..3 kv_full, 4..7 kv_empty, 8..11 q_full[g][item parity], 12..15 q_empty, then [g*2 + buf] families:
+  // 16 s_full, 20 s_empty, 24 p_full, 28 p_empty, 32 o_full, 36 o_empty; slot 44: TMEM base
+  const int KV_FULL = 0, KV_EMPTY = 4, Q_FULL = 8, Q_EMPTY = 12, S_FULL = 16, S_EMPTY = 20, P_FULL = 24, P_EMPTY = 28,
+            O_FULL = 32, O_EMPTY = 36;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 44);
   if (threadIdx.x == 0) {
     for (int i = 0; i < ATT_STAGES; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), 1); }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(BAR(Q_FULL + g), 1); mbar_init(BAR(Q_EMPTY + g), 1);
-      mbar_init(BAR(S_FULL + g), 1); mbar_init(BAR(S_EMPTY + g), 128);
-      mbar_init(BAR(P_FULL + g), 128); mbar_init(BAR(P_EMPTY + g), 1);
-      for (int b = 0; b < 2; ++b) { mbar_init(BAR(O_FULL + g * 2 + b), 1); mbar_init(BAR(O_EMPTY + g * 2 + b), 128); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), 1);
+      mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_EMPTY + i), 128);
+      mbar_init(BAR(P_FULL + i), 128); mbar_init(BAR(P_EMPTY + i), 1);
+      mbar_init(BAR(O_FULL + i), 1); mbar_init(BAR(O_EMPTY + i), 128);
     }
     fence_barrier_init();
   }
@@ -66,22 +67,26 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t o_col0 = 256;  // S[0] 0..127, S[1] 128..255, O_j[g][buf] at 256 + (g*2+buf)*HDP
+  // TMEM columns: S[g][buf] at (g*2+buf)*64 (4 x 64), O_u[g][buf] at 256 + (g*2+buf)*HDP
+  const uint32_t o_col0 = 256;
   const size_t which_stride = (size_t)p.nseq * p.heads * NTL * HDP * 128;   // elements between q, k, v planes
 
   if (warp == 0) {
     // ===================== loader =====================
     if (lane == 0) {
-      uint32_t kslot = 0, kph = 0, qph[2] = {0, 0};
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      uint32_t kslot = 0, kph = 0, qph = 0;    // qph: bit (g*2 + b) = phase of Q buffer [g][b]
+      int n_local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
         const int pair = item % p.NP, sh = item / p.NP;            // sh = seq * heads + head
         const __nv_bfloat16* qb = p.qkv + (size_t)sh * NTL * HDP * 128;
         const int nq = min(2, NTL - 2 * pair);
+        const int b = n_local & 1;
         for (int g = 0; g < nq; ++g) {
-          mbar_wait(BAR(Q_EMPTY + g), qph[g] ^ 1);
-          qph[g] ^= 1;
-          mbar_arrive_expect_tx(BAR(Q_FULL + g), tile_bytes);
-          bulk_g2s(sbase + off_q + g * tile_bytes, qb + (size_t)(2 * pair + g) * HDP * 128, tile_bytes, BAR(Q_FULL + g));
+          const int qi = g * 2 + b;
+          mbar_wait(BAR(Q_EMPTY + qi), ((qph >> qi) & 1) ^ 1);
+          qph ^= 1u << qi;
+          mbar_arrive_expect_tx(BAR(Q_FULL + qi), tile_bytes);
+          bulk_g2s(sbase + off_q + qi * tile_bytes, qb + (size_t)(2 * pair + g) * HDP * 128, tile_bytes, BAR(Q_FULL + qi));
         }
         for (int j = 0; j < NTL; ++j) {
           mbar_wait(BAR(KV_EMPTY + kslot), kph ^ 1);
@@ -95,55 +100,87 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Work is cut into units of 64 keys (half a K/V tile).  S for unit u+1 (next half tile, or unit 0 of the next
+    // item) is issued BEFORE P.V of unit u and S / P / O are double-buffered per group, so a softmax group never
+    // waits on the tensor pipe in steady state.
     if (lane == 0) {
-      const uint32_t idesc_s = instr_desc(128, 128), idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
+      const uint32_t idesc_s = instr_desc(128, 64), idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
       const uint32_t hi_k = (128u >> 4) | (1u << 14);              // K-major tiles: SBO = 128 B
-      const uint32_t lo_k = 128u << 16;                            //                LBO = 128 rows * 16 B
+      const uint32_t lo_k = 128u << 16;                            //   128-row tiles: LBO = 128 rows * 16 B
+      const uint32_t lo_p = 128u << 16;                            //   P half tile is 128 rows too
       const uint32_t hi_v = ((128u * 16) >> 4) | (1u << 14);       // V as MN-major: SBO = 2048 B (next 8 columns)
       const uint32_t lo_v = (128u >> 4) << 16;                     //                LBO = 128 B (next 8 kv rows)
       const uint32_t q16 = (sbase + off_q) >> 4, kv16 = (sbase + off_kv) >> 4, p16 = (sbase + off_p) >> 4;
       const uint32_t tile16 = tile_bytes >> 4, pt16 = p_bytes >> 4;
-      uint32_t kslot = 0, kph = 0, qph[2] = {0, 0};
-      uint32_t sph[2] = {0, 0}, pph[2] = {0, 0}, oph[2][2] = {{0, 0}, {0, 0}};
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int pair = item % p.NP;
-        const int nq = min(2, NTL - 2 * pair);
-        auto issue_s = [&](int g, uint32_t slot) {
-          mbar_wait(BAR(S_EMPTY + g), sph[g] ^ 1);
-          tc_fence_after();
-          const uint32_t qa = q16 + g * tile16, kb = kv16 + slot * 2 * tile16;
-          for (int kk = 0; kk < HDP / 16; ++kk)
-            mma_lohi(tmem + g * 128, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc_s, (uint32_t)kk);
-          mma_commit(BAR(S_FULL + g));
-          sph[g] ^= 1;
-        };
-        for (int g = 0; g < nq; ++g) { mbar_wait(BAR(Q_FULL + g), qph[g]); qph[g] ^= 1; }
+      uint32_t kslot = 0, kph = 0;
+      uint32_t qph = 0, sph = 0, pph = 0, oph = 0;   // phase bits indexed [g*2 + buf]
+      uint32_t us[2] = {0, 0};                       // per-group running unit counter on the S-issue side
+      uint32_t up[2] = {0, 0};                       // ... and on the P.V side
+      auto issue_s = [&](int g, int b, uint32_t slot, int half, bool last_of_item) {
+        const int si = g * 2 + (int)(us[g] & 1);
+        ++us[g];
+        mbar_wait(BAR(S_EMPTY + si), ((sph >> si) & 1) ^ 1);
+        sph ^= 1u << si;
+        tc_fence_after();
+        const uint32_t qa = q16 + (g * 2 + b) * tile16, kb = kv16 + slot * 2 * tile16 + half * 64;
+        for (int kk = 0; kk < HDP / 16; ++kk)
+          mma_lohi(tmem + si * 64, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc_s, (uint32_t)kk);
+        mma_commit(BAR(S_FULL + si));
+        if (last_of_item) mma_commit(BAR(Q_EMPTY + g * 2 + b));
+      };
+      auto wait_q = [&](int g, int b) {
+        const int qi = g * 2 + b;
+        mbar_wait(BAR(Q_FULL + qi), (qph >> qi) & 1);
+        qph ^= 1u << qi;
+      };
+      int n_local = 0;
+      if ((int)blockIdx.x < p.n_items) {   // prologue: S of the very first unit
+        const int nq = min(2, NTL - 2 * ((int)blockIdx.x % p.NP));
+        for (int g = 0; g < nq; ++g) wait_q(g, 0);
         mbar_wait(BAR(KV_FULL + kslot), kph);
         tc_fence_after();
-        for (int g = 0; g < nq; ++g) issue_s(g, kslot);
-        for (int j = 0; j < NTL; ++j) {
+        for (int g = 0; g < nq; ++g) issue_s(g, 0, kslot, 0, NU == 1);
+      }
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
+        const int nq = min(2, NTL - 2 * (item % p.NP));
+        const int b = n_local & 1;
+        const int next = item + gridDim.x;
+        const int nq_next = next < p.n_items ? min(2, NTL - 2 * (next % p.NP)) : 0;
+        for (int u = 0; u < NU; ++u) {
+          const int half = u & 1;
           uint32_t nslot = kslot + 1, nph = kph;
           if (nslot == ATT_STAGES) { nslot = 0; nph ^= 1; }
-          const bool more = j + 1 < NTL;
-          if (more) { mbar_wait(BAR(KV_FULL + nslot), nph); tc_fence_after(); }
-          for (int g = 0; g < nq; ++g) {
-            mbar_wait(BAR(P_FULL + g), pph[g]);        // softmax of tile j done (S[g] was released before)
-            pph[g] ^= 1;
-            if (more) issue_s(g, nslot);
-            else if (g == nq - 1) for (int gg = 0; gg < nq; ++gg) mma_commit(BAR(Q_EMPTY + gg));  // all S MMAs issued
-            const int ob = j & 1;
-            mbar_wait(BAR(O_EMPTY + g * 2 + ob), oph[g][ob] ^ 1);
-            oph[g][ob] ^= 1;
+          // ---- S for the next unit ----
+          if (u + 1 < NU) {
+            if (half == 1) { mbar_wait(BAR(KV_FULL + nslot), nph); tc_fence_after(); }
+            for (int g = 0; g < nq; ++g) issue_s(g, b, half == 1 ? nslot : kslot, half ^ 1, u + 2 == NU);
+          } else if (nq_next > 0) {
+            for (int g = 0; g < nq_next; ++g) wait_q(g, b ^ 1);
+            mbar_wait(BAR(KV_FULL + nslot), nph);
             tc_fence_after();
-            const uint32_t pa = p16 + g * pt16, vb = kv16 + kslot * 2 * tile16 + tile16;
-            for (int kk = 0; kk < 8; ++kk)
-              mma_lohi(tmem + o_col0 + (g * 2 + ob) * HDP, (pa + kk * 2 * 128) | lo_k, hi_k, (vb + kk * 16) | lo_v, hi_v,
-                       idesc_pv, (uint32_t)kk);
-            mma_commit(BAR(O_FULL + g * 2 + ob));
-            mma_commit(BAR(P_EMPTY + g));
+            for (int g = 0; g < nq_next; ++g) issue_s(g, b ^ 1, nslot, 0, NU == 1);
           }
-          mma_commit(BAR(KV_EMPTY + kslot));
-          kslot = nslot; kph = nph;
+          // ---- O_u = P_u . V[64 keys of this unit] ----
+          for (int g = 0; g < nq; ++g) {
+            const int bi = g * 2 + (int)(up[g] & 1);
+            ++up[g];
+            mbar_wait(BAR(P_FULL + bi), (pph >> bi) & 1);
+            pph ^= 1u << bi;
+            mbar_wait(BAR(O_EMPTY + bi), ((oph >> bi) & 1) ^ 1);
+            oph ^= 1u << bi;
+            tc_fence_after();
+            const uint32_t pa = p16 + bi * pt16, vb = kv16 + kslot * 2 * tile16 + tile16 + half * 64;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma_lohi(tmem + o_col0 + bi * HDP, (pa + kk * 2 * 128) | lo_p, hi_k, (vb + kk * 16) | lo_v, hi_v, idesc_pv,
+                       (uint32_t)kk);
+            mma_commit(BAR(O_FULL + bi));
+            mma_commit(BAR(P_EMPTY + bi));
+          }
+          if (half == 1 || u + 1 == NU) {          // both halves of this K/V stage consumed
+            mma_commit(BAR(KV_EMPTY + kslot));
+            kslot = nslot; kph = nph;
+          }
         }
       }
     }
@@ -153,76 +190,81 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* pt = smem + off_p + (size_t)g * p_bytes;
-    uint32_t sph = 0, pph = 0, oph[2] = {0, 0};
+    uint32_t sph = 0, pph = 0, oph = 0;         // phase bits per buffer (bit = buf)
+    uint32_t uc = 0;                            // running unit counter of this group
     const int OC = HDP / 8;                     // 16-byte chunks per output row and head
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int pair = item % p.NP, sh = item / p.NP;
       const int nq = min(2, NTL - 2 * pair);
       if (g >= nq) continue;
       const int qt = 2 * pair + g;
-      float m_run = -INFINITY, l_run = 0.f, alpha = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;
       float o[32];
 #pragma unroll
       for (int d = 0; d < 32; ++d) o[d] = 0.f;
-      auto fold = [&](int ob) {               // o += O_j of the previous tile
-        mbar_wait(BAR(O_FULL + g * 2 + ob), oph[ob]);
-        oph[ob] ^= 1;
+      auto fold = [&](int ob) {               // o += O of the previous unit
+        const int bi = g * 2 + ob;
+        mbar_wait(BAR(O_FULL + bi), (oph >> ob) & 1);
+        oph ^= 1u << ob;
         tc_fence_after();
-        for (int c0 = 0; c0 < HDP; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(lane_addr + o_col0 + (g * 2 + ob) * HDP + c0, r);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) if (c0 + e < 32) o[(c0 + e) & 31] += __uint_as_float(r[e]);
-        }
-        tc_fence_before();
-        mbar_arrive(BAR(O_EMPTY + g * 2 + ob));
-      };
-      for (int j = 0; j < NTL; ++j) {
-        mbar_wait(BAR(S_FULL + g), sph);
-        sph ^= 1;
-        tc_fence_after();
-        uint32_t s[128];
-        tmem_ld32(lane_addr + g * 128, s);
-        tmem_ld32(lane_addr + g * 128 + 32, s + 32);
-        tmem_ld32(lane_addr + g * 128 + 64, s + 64);
-        tmem_ld32(lane_addr + g * 128 + 96, s + 96);
+        uint32_t r[32];
+        tmem_ld16(lane_addr + o_col0 + bi * HDP, r);
+        if (HDP > 16) tmem_ld16(lane_addr + o_col0 + bi * HDP + 16, r + 16);
         tc_wait_ld();
         tc_fence_before();
-        mbar_arrive(BAR(S_EMPTY + g));
-        const int valid = min(128, p.L - j * 128);
-        float mx = m_run;
+        mbar_arrive(BAR(O_EMPTY + bi));
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          if (i >= valid) s[i] = 0xff800000u;  // -inf
-          mx = fmaxf(mx, __uint_as_float(s[i]));
+        for (int e = 0; e < 32; ++e) if (e < HDP) o[e] += __uint_as_float(r[e]);
+      };
+      for (int u = 0; u < NU; ++u, ++uc) {
+        const int buf = (int)(uc & 1), bi = g * 2 + buf;
+        mbar_wait(BAR(S_FULL + bi), (sph >> buf) & 1);
+        sph ^= 1u << buf;
+        tc_fence_after();
+        uint32_t s[64];
+        tmem_ld32(lane_addr + bi * 64, s);
+        tmem_ld32(lane_addr + bi * 64 + 32, s + 32);
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(BAR(S_EMPTY + bi));
+        const int valid = p.L - u * 64;
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = 0xff800000u;  // -inf: key rows beyond the sequence
         }
-        alpha = fast_exp2(m_run - mx);
-        m_run = mx;
-        float rs = 0.f;
-        mbar_wait(BAR(P_EMPTY + g), pph ^ 1);   // P.V of the previous tile has consumed the P buffer
-        pph ^= 1;
+        float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int i = 0; i < 64; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i])); mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const float alpha = fast_exp2(m_run - mx);
+        m_run = mx;
+        float rs0 = 0.f, rs1 = 0.f;
+        mbar_wait(BAR(P_EMPTY + bi), ((pph >> buf) & 1) ^ 1);   // P.V two units ago has consumed this P buffer
+        pph ^= 1u << buf;
+        uint8_t* pt = smem + off_p + (size_t)bi * p_bytes;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float p0 = fast_exp2(__uint_as_float(s[c * 8 + 2 * e]) - mx);
             const float p1 = fast_exp2(__uint_as_float(s[c * 8 + 2 * e + 1]) - mx);
-            rs += p0 + p1;
+            rs0 += p0; rs1 += p1;
             w[e] = pack_bf16(p0, p1);
           }
           *reinterpret_cast<uint4*>(pt + ((size_t)c * 128 + m) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         fence_proxy_async();
-        mbar_arrive(BAR(P_FULL + g));
-        if (j > 0) fold((j - 1) & 1);
-        l_run = l_run * alpha + rs;
+        mbar_arrive(BAR(P_FULL + bi));
+        if (u > 0) fold(buf ^ 1);
+        l_run = l_run * alpha + (rs0 + rs1);
 #pragma unroll
         for (int d = 0; d < 32; ++d) o[d] *= alpha;
       }
-      fold((NTL - 1) & 1);
+      fold((int)((uc - 1) & 1));
       // ---- normalise and store this head's slice of the o image ----
       const int s_idx = sh / p.heads, h = sh - s_idx * p.heads;
       const float inv = 1.f / l_run;
@@ -241,7 +283,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
 }
 
 inline uint32_t attn_tc_smem(int HDP) {
-  return (uint32_t)(2 + ATT_STAGES * 2) * HDP * 128 * 2 + 2 * 128 * 128 * 2 + 512;
+  return (uint32_t)(4 + ATT_STAGES * 2) * HDP * 128 * 2 + 4 * 128 * 64 * 2 + 512;
 }
 
 // --------------------------------------------------------------------------------------------
