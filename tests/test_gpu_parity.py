@@ -206,3 +206,17 @@ def test_segment_ola_matches_oracle(pkg):
         chunk = seg[i0:i0 + 2].permute(1, 0, 2).contiguous().cuda()
         pkg.segment_ola(chunk, i0, len(starts), track)
     _check(track, want, maxabs=1e-5, sisdr=100.0, what="segment_ola")
+
+
+def test_full_track_segments_match_oracle_stitch(pkg):
+    """BASELINE config 3 in miniature: chunked inference with 50 % overlap == oracle forward per segment + oracle stitch."""
+    from mss_tf_locoformer_b200.segments import separate_track
+    cfg, sd, arr, model = _mss(pkg, "mss_hop2_macaron")
+    track = _mixture(5000, 1)[0]
+    seg = 1024
+    want = oracle.separate_track(lambda x: oracle.mss_forward(sd, cfg, x), track, seg, batch=2)
+    with torch.no_grad():
+        got = separate_track(model, track.cuda(), seg_len=seg, batch=3)
+    assert list(got) == list(want)
+    for k in want:
+        _check(got[k], want[k], what=f"track/{k}")
