@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
   const size_t which_stride = (size_t)p.nseq * p.heads * NTL * HDP * 128;   // elements between q, k, v planes
 
   if (warp == 0) {
-    // ===================== loader =====================
-    if (lane == 0) {
+    // ===================== loader (whole warp runs the loop, one elected lane issues) =====================
+    {
       uint32_t kslot = 0, kph = 0, qph = 0;    // qph: bit (g*2 + b) = phase of Q buffer [g][b]
       int n_local = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
@@ -85,15 +85,21 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
           const int qi = g * 2 + b;
           mbar_wait(BAR(Q_EMPTY + qi), ((qph >> qi) & 1) ^ 1);
           qph ^= 1u << qi;
-          mbar_arrive_expect_tx(BAR(Q_FULL + qi), tile_bytes);
-          bulk_g2s(sbase + off_q + qi * tile_bytes, qb + (size_t)(2 * pair + g) * HDP * 128, tile_bytes, BAR(Q_FULL + qi));
+          if (elect_one()) {
+            mbar_arrive_expect_tx(BAR(Q_FULL + qi), tile_bytes);
+            bulk_g2s(sbase + off_q + qi * tile_bytes, qb + (size_t)(2 * pair + g) * HDP * 128, tile_bytes, BAR(Q_FULL + qi));
+          }
+          __syncwarp();
         }
         for (int j = 0; j < NTL; ++j) {
           mbar_wait(BAR(KV_EMPTY + kslot), kph ^ 1);
-          mbar_arrive_expect_tx(BAR(KV_FULL + kslot), 2 * tile_bytes);
-          const uint32_t dst = sbase + off_kv + kslot * 2 * tile_bytes;
-          bulk_g2s(dst, qb + which_stride + (size_t)j * HDP * 128, tile_bytes, BAR(KV_FULL + kslot));
-          bulk_g2s(dst + tile_bytes, qb + 2 * which_stride + (size_t)j * HDP * 128, tile_bytes, BAR(KV_FULL + kslot));
+          if (elect_one()) {
+            mbar_arrive_expect_tx(BAR(KV_FULL + kslot), 2 * tile_bytes);
+            const uint32_t dst = sbase + off_kv + kslot * 2 * tile_bytes;
+            bulk_g2s(dst, qb + which_stride + (size_t)j * HDP * 128, tile_bytes, BAR(KV_FULL + kslot));
+            bulk_g2s(dst + tile_bytes, qb + 2 * which_stride + (size_t)j * HDP * 128, tile_bytes, BAR(KV_FULL + kslot));
+          }
+          __syncwarp();
           if (++kslot == ATT_STAGES) { kslot = 0; kph ^= 1; }
         }
       }
@@ -102,8 +108,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
     // ===================== MMA issuer =====================
     // Work is cut into units of 64 keys (half a K/V tile).  S for unit u+1 (next half tile, or unit 0 of the next
     // item) is issued BEFORE P.V of unit u and S / P / O are double-buffered per group, so a softmax group never
-    // waits on the tensor pipe in steady state.
-    if (lane == 0) {
+    // waits on the tensor pipe in steady state.  The whole warp runs the control flow; one elected lane issues.
+    {
       const uint32_t idesc_s = instr_desc(128, 64), idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
       const uint32_t hi_k = (128u >> 4) | (1u << 14);              // K-major tiles: SBO = 128 B
       const uint32_t lo_k = 128u << 16;                            //   128-row tiles: LBO = 128 rows * 16 B
@@ -123,10 +129,13 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
         sph ^= 1u << si;
         tc_fence_after();
         const uint32_t qa = q16 + (g * 2 + b) * tile16, kb = kv16 + slot * 2 * tile16 + half * 64;
-        for (int kk = 0; kk < HDP / 16; ++kk)
-          mma_lohi(tmem + si * 64, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc_s, (uint32_t)kk);
-        mma_commit(BAR(S_FULL + si));
-        if (last_of_item) mma_commit(BAR(Q_EMPTY + g * 2 + b));
+        if (elect_one()) {
+          for (int kk = 0; kk < HDP / 16; ++kk)
+            mma_lohi(tmem + si * 64, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc_s, (uint32_t)kk);
+          mma_commit(BAR(S_FULL + si));
+          if (last_of_item) mma_commit(BAR(Q_EMPTY + g * 2 + b));
+        }
+        __syncwarp();
       };
       auto wait_q = [&](int g, int b) {
         const int qi = g * 2 + b;
@@ -170,15 +179,19 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
             oph ^= 1u << bi;
             tc_fence_after();
             const uint32_t pa = p16 + bi * pt16, vb = kv16 + kslot * 2 * tile16 + tile16 + half * 64;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma_lohi(tmem + o_col0 + bi * HDP, (pa + kk * 2 * 128) | lo_p, hi_k, (vb + kk * 16) | lo_v, hi_v, idesc_pv,
-                       (uint32_t)kk);
-            mma_commit(BAR(O_FULL + bi));
-            mma_commit(BAR(P_EMPTY + bi));
+              for (int kk = 0; kk < 4; ++kk)
+                mma_lohi(tmem + o_col0 + bi * HDP, (pa + kk * 2 * 128) | lo_p, hi_k, (vb + kk * 16) | lo_v, hi_v, idesc_pv,
+                         (uint32_t)kk);
+              mma_commit(BAR(O_FULL + bi));
+              mma_commit(BAR(P_EMPTY + bi));
+            }
+            __syncwarp();
           }
           if (half == 1 || u + 1 == NU) {          // both halves of this K/V stage consumed
-            mma_commit(BAR(KV_EMPTY + kslot));
+            if (elect_one()) mma_commit(BAR(KV_EMPTY + kslot));
+            __syncwarp();
             kslot = nslot; kph = nph;
           }
         }
@@ -367,7 +380,7 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
       for (int i = 0; i < 3; ++i) bulk_g2s(sbase + off_w + i * part_bytes, p.wimg + (size_t)i * part_bytes, part_bytes, BAR(W_FULL));
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = instr_desc(128, NPART);
       const uint32_t hi = (128u >> 4) | (1u << 14);
       const uint32_t lo_a = 128u << 16, lo_b = (uint32_t)NPART << 16;
@@ -379,12 +392,16 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
         for (int part = 0; part < 3; ++part) {
           mbar_wait(BAR(D_EMPTY + part), (uint32_t)((it & 1) ^ 1));
           tc_fence_after();
-          for (int kk = 0; kk < C / 16; ++kk)
-            mma_lohi(tmem + part * NPART, (a16 + slot * as16 + kk * 2 * 128) | lo_a, hi,
-                     (w16 + part * ps16 + kk * 2 * NPART) | lo_b, hi, idesc, (uint32_t)kk);
-          mma_commit(BAR(D_FULL + part));
+          if (elect_one()) {
+            for (int kk = 0; kk < C / 16; ++kk)
+              mma_lohi(tmem + part * NPART, (a16 + slot * as16 + kk * 2 * 128) | lo_a, hi,
+                       (w16 + part * ps16 + kk * 2 * NPART) | lo_b, hi, idesc, (uint32_t)kk);
+            mma_commit(BAR(D_FULL + part));
+          }
+          __syncwarp();
         }
-        mma_commit(BAR(A_EMPTY + slot));
+        if (elect_one()) mma_commit(BAR(A_EMPTY + slot));
+        __syncwarp();
         if (++slot == 3) { slot = 0; aph ^= 1; }
       }
     }
@@ -514,17 +531,22 @@ __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
     if (lane == 0) {
       mbar_arrive_expect_tx(BAR(W_FULL), w_bytes);
       bulk_g2s(sbase + off_w, p.wimg, w_bytes, BAR(W_FULL));
+    }
+    {
       uint32_t slot = 0, ph = 0;
       for (int it = 0; it < n_iter; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
-        mbar_arrive_expect_tx(BAR(A_FULL + slot), a_bytes);
-        bulk_g2s(sbase + off_a + slot * a_bytes, p.oimg + (size_t)tile * AP * 128, a_bytes, BAR(A_FULL + slot));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(BAR(A_FULL + slot), a_bytes);
+          bulk_g2s(sbase + off_a + slot * a_bytes, p.oimg + (size_t)tile * AP * 128, a_bytes, BAR(A_FULL + slot));
+        }
+        __syncwarp();
         if (++slot == PROJ_STAGES) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = instr_desc(128, C);
       const uint32_t hi = (128u >> 4) | (1u << 14);
       const uint32_t lo_a = 128u << 16, lo_b = (uint32_t)C << 16;
@@ -536,11 +558,14 @@ __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
         mbar_wait(BAR(A_FULL + slot), ph);
         mbar_wait(BAR(D_EMPTY + buf), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
-        for (int kk = 0; kk < AP / 16; ++kk)
-          mma_lohi(tmem + buf * C, (a16 + slot * as16 + kk * 2 * 128) | lo_a, hi, (w16 + kk * 2 * C) | lo_b, hi, idesc,
-                   (uint32_t)kk);
-        mma_commit(BAR(D_FULL + buf));
-        mma_commit(BAR(A_EMPTY + slot));
+        if (elect_one()) {
+          for (int kk = 0; kk < AP / 16; ++kk)
+            mma_lohi(tmem + buf * C, (a16 + slot * as16 + kk * 2 * 128) | lo_a, hi, (w16 + kk * 2 * C) | lo_b, hi, idesc,
+                     (uint32_t)kk);
+          mma_commit(BAR(D_FULL + buf));
+          mma_commit(BAR(A_EMPTY + slot));
+        }
+        __syncwarp();
         if (++slot == PROJ_STAGES) { slot = 0; ph ^= 1; }
       }
     }

@@ -191,22 +191,25 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   const uint32_t d2_col0 = 2u * 2 * TC_HC;  // after the two D1 tiles
 
   if (warp == 0) {
-    // ===================== weight loader =====================
-    if (lane == 0) {
+    // ===================== weight loader (whole warp runs the loop, one elected lane issues) =====================
+    {
       uint32_t slot = 0, ph = 0;
       for (int it = 0; it < n_iter; ++it) {
         const char* src = p.img;
         for (int s = 0; s < stages_per_iter; ++s, src += g.stage_bytes) {
           mbar_wait(BAR(W_EMPTY + slot), ph ^ 1);
-          mbar_arrive_expect_tx(BAR(W_FULL + slot), g.stage_bytes);
-          bulk_g2s(sbase + g.off_w + slot * g.stage_bytes, src, g.stage_bytes, BAR(W_FULL + slot));
+          if (elect_one()) {
+            mbar_arrive_expect_tx(BAR(W_FULL + slot), g.stage_bytes);
+            bulk_g2s(sbase + g.off_w + slot * g.stage_bytes, src, g.stage_bytes, BAR(W_FULL + slot));
+          }
+          __syncwarp();
           if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp runs the control flow; elected lane issues) =====================
+    {
       const uint32_t idesc1 = instr_desc(128, 2 * TC_HC), idesc2 = instr_desc(128, C);
       // descriptor words: lo = (addr >> 4) | (LBO/16 << 16); hi = SBO/16 | version(1) << 14
       const uint32_t hi = (128u >> 4) | (1u << 14);
@@ -238,16 +241,23 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
               for (int tl = 0; tl < TPS; ++tl) {
                 const int tap = s * TPS + tl;
                 if (tap >= KT) break;
+                if (elect_one()) {
 #pragma unroll
-                for (uint32_t kk = 0; kk < TC_HC / 16; ++kk)
-                  mma_lohi(dcol, (gb + tap + kk * 2 * AR) | lo_a, hi, (wb + tl * tap16 + kk * 2 * C) | lo_b2, hi, idesc2,
-                           (uint32_t)(cc | tap | (int)kk));
+                  for (uint32_t kk = 0; kk < TC_HC / 16; ++kk)
+                    mma_lohi(dcol, (gb + tap + kk * 2 * AR) | lo_a, hi, (wb + tl * tap16 + kk * 2 * C) | lo_b2, hi, idesc2,
+                             (uint32_t)(cc | tap | (int)kk));
+                }
+                __syncwarp();
               }
             }
-            mma_commit(BAR(W_EMPTY + wslot));
+            if (elect_one()) mma_commit(BAR(W_EMPTY + wslot));
+            __syncwarp();
             if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
           }
-          _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(G_EMPTY + t));
+          if (elect_one()) {
+            _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(G_EMPTY + t));
+          }
+          __syncwarp();
         };
         for (int c = 0; c < NC; ++c) {
           _Pragma("unroll") for (int t = 0; t < NT; ++t) {
@@ -263,22 +273,32 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
               _Pragma("unroll") for (int t = 0; t < NT; ++t) {
                 const uint32_t ab = a16 + aslot[t] * aslot16 + k + hf * KK1 * 2 * AR;
                 const uint32_t dcol = tmem + t * (2 * TC_HC);
-                for (uint32_t kk = 0; kk < KK1; ++kk)
-                  mma_lohi(dcol, (ab + kk * 2 * AR) | lo_a, hi, (wb + kk * 2 * 128) | lo_b1, hi, idesc1,
-                           (uint32_t)(k | hf | (int)kk));
+                if (elect_one()) {
+                  for (uint32_t kk = 0; kk < KK1; ++kk)
+                    mma_lohi(dcol, (ab + kk * 2 * AR) | lo_a, hi, (wb + kk * 2 * 128) | lo_b1, hi, idesc1,
+                             (uint32_t)(k | hf | (int)kk));
+                }
+                __syncwarp();
               }
-              mma_commit(BAR(W_EMPTY + wslot));
+              if (elect_one()) mma_commit(BAR(W_EMPTY + wslot));
+              __syncwarp();
               if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
             }
-          _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(D1_FULL + t));
-          if (c == NC - 1)
-            _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(A_EMPTY + aslot[t]));
+          if (elect_one()) {
+            _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(D1_FULL + t));
+            if (c == NC - 1)
+              _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(A_EMPTY + aslot[t]));
+          }
+          __syncwarp();
           if (c > 0) mma2(c - 1, qpar ^ 1);
           qpar ^= 1;
         }
         mma2(NC - 1, qpar ^ 1);
+        if (elect_one()) {
+          _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(D2_FULL + t));
+        }
+        __syncwarp();
         _Pragma("unroll") for (int t = 0; t < NT; ++t) {
-          mma_commit(BAR(D2_FULL + t));
           for (int a = 0; a < NT; ++a)   // advance this tile's A slot by NT positions in the NA ring
             if (++aslot[t] == (uint32_t)NA) { aslot[t] = 0; aph[t] ^= 1; }
         }
