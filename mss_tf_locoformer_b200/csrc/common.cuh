@@ -82,7 +82,7 @@ struct PathPack {
   size_t tc_qkv, tc_wo;
 };
 struct PackLayout {
-  size_t enc_w /*[3][3][Cin][C]*/, enc_b, gln_w, gln_b, dec_w /*[3][3][C][2S] flipped*/, dec_b;
+  size_t enc_w /*[3][3][Cin][C]*/, enc_b, gln_w, gln_b, dec_w /*[9 taps][8 outputs][C]*/, dec_b;
   size_t twiddle /*[n_fft/2] float2*/, window /*[n_fft]*/;
   std::vector<PathPack> paths;  // [2*layer + axis]
   size_t total;

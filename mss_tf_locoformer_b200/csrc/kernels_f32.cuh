@@ -470,14 +470,15 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
 
 // --------------------------------------------------------------------------------------
 // K6 decoder: ConvTranspose2d(C, 2S, 3x3, pad 1) as a 9-tap gather (:182); one warp per
-// position, lanes over channels, shuffle reduction; writes est[b][src][t][f][re/im].
-// wd layout: [9 taps][C][8] (tap = dt*3+df multiplies x[t+1-dt, f+1-df]).
+// position, lanes over channels (conflict-free float4 weight reads), shuffle reduction;
+// writes est[b][src][t][f][re/im].  wd layout: [9 taps][8 outputs][C] (tap = dt*3+df
+// multiplies x[t+1-dt, f+1-df]).
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dec_conv_kernel(const float* __restrict__ x, int n_frames, int n_freq, int C,
                                                        int n_out, const float* __restrict__ wd,
                                                        const float* __restrict__ bias, float* __restrict__ est,
                                                        long long n_pos) {
-  extern __shared__ float wsm[];  // 9*C*8
+  extern __shared__ float wsm[];  // 9*8*C
   for (int i = threadIdx.x; i < 9 * C * 8; i += blockDim.x) wsm[i] = wd[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -498,18 +499,13 @@ __global__ void __launch_bounds__(256) dec_conv_kernel(const float* __restrict__
         const int ff = f + 1 - df;
         if (ff < 0 || ff >= n_freq) continue;
         const float* px = x + (((size_t)b * n_frames + tt) * n_freq + ff) * C;
-        const float* pw = wsm + (dt * 3 + df) * C * 8;
+        const float* pw = wsm + (dt * 3 + df) * 8 * C;
         for (int c = lane << 2; c < C; c += 128) {
           const float4 xv = __ldg(reinterpret_cast<const float4*>(px + c));
-          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const float4 w0 = *reinterpret_cast<const float4*>(pw + (c + ci) * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(pw + (c + ci) * 8 + 4);
-            acc[0] = fmaf(xs[ci], w0.x, acc[0]); acc[1] = fmaf(xs[ci], w0.y, acc[1]);
-            acc[2] = fmaf(xs[ci], w0.z, acc[2]); acc[3] = fmaf(xs[ci], w0.w, acc[3]);
-            acc[4] = fmaf(xs[ci], w1.x, acc[4]); acc[5] = fmaf(xs[ci], w1.y, acc[5]);
-            acc[6] = fmaf(xs[ci], w1.z, acc[6]); acc[7] = fmaf(xs[ci], w1.w, acc[7]);
+          for (int o = 0; o < 8; ++o) {
+            const float4 w = *reinterpret_cast<const float4*>(pw + o * C + c);
+            acc[o] = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, fmaf(xv.w, w.w, acc[o]))));
           }
         }
       }

@@ -26,7 +26,7 @@ static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; 
 
 // ---- generic strided-permute copy used by the weight packer ---------------------------
 struct Permute {
-  int n[4]; long long s[4]; long long offset; int last_valid;
+  int n[4]; long long s[4]; long long offset; int last_valid; int dim2_valid;
 };
 __global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, Permute p) {
   const long long total = (long long)p.n[0] * p.n[1] * p.n[2] * p.n[3];
@@ -36,12 +36,12 @@ __global__ void permute_kernel(const float* __restrict__ src, float* __restrict_
     const int i2 = (int)(r % p.n[2]); r /= p.n[2];
     const int i1 = (int)(r % p.n[1]); r /= p.n[1];
     const int i0 = (int)r;
-    dst[i] = (i3 < p.last_valid) ? src[p.offset + i0 * p.s[0] + i1 * p.s[1] + i2 * p.s[2] + i3 * p.s[3]] : 0.f;
+    dst[i] = (i3 < p.last_valid && i2 < p.dim2_valid) ? src[p.offset + i0 * p.s[0] + i1 * p.s[1] + i2 * p.s[2] + i3 * p.s[3]] : 0.f;
   }
 }
 static void permute(const float* src, float* dst, int n0, int n1, int n2, int n3, long long s0, long long s1,
-                    long long s2, long long s3, long long offset, int last_valid, cudaStream_t st) {
-  Permute p{{n0, n1, n2, n3}, {s0, s1, s2, s3}, offset, last_valid < 0 ? n3 : last_valid};
+                    long long s2, long long s3, long long offset, int last_valid, cudaStream_t st, int dim2_valid = -1) {
+  Permute p{{n0, n1, n2, n3}, {s0, s1, s2, s3}, offset, last_valid < 0 ? n3 : last_valid, dim2_valid < 0 ? n2 : dim2_valid};
   const long long total = (long long)n0 * n1 * n2 * n3;
   const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
   permute_kernel<<<blocks, 256, 0, st>>>(src, dst, p);
@@ -196,8 +196,8 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
                                                 (pl->head_dim + 15) / 16 * 16);
     }
   if (c.enc_in_ch > 0) {
-    // deconv.weight [C, 2S, 3, 3] -> [9][C][8]
-    permute(w[i++], dst(L.dec_w), 1, 9, C, 8, 0, 1, (long long)S2 * 9, 9, 0, S2, st);
+    // deconv.weight [C, 2S, 3, 3] -> [9][8][C] (outputs >= 2S stay zero from the memset)
+    permute(w[i++], dst(L.dec_w), 1, 9, 8, C, 0, 1, 9, (long long)S2 * 9, 0, -1, st, S2);
     copy(w[i++], L.dec_b, S2);
   }
   if (c.n_fft > 0)
