@@ -35,7 +35,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
+__global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
             O_FULL = 32, O_EMPTY = 36;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 44);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < ATT_STAGES; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), 1); }
+    for (int i = 0; i < ATT_STAGES; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), 2); }
     for (int i = 0; i < 4; ++i) {
       mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), 1);
       mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_EMPTY + i), 128);
@@ -104,29 +104,30 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers: one warp per query-tile group =====================
     // Work is cut into units of 64 keys (half a K/V tile).  S for unit u+1 (next half tile, or unit 0 of the next
-    // item) is issued BEFORE P.V of unit u and S / P / O are double-buffered per group, so a softmax group never
-    // waits on the tensor pipe in steady state.  The whole warp runs the control flow; one elected lane issues.
+    // item) is issued BEFORE P.V of unit u and S / P / O are double-buffered, so a softmax group never waits on the
+    // tensor pipe in steady state.  The whole warp runs the control flow; one elected lane issues.
+    // Ordering that makes extra barriers unnecessary: the softmax group folds O(u-1) before it publishes P(u+1),
+    // so "P(u) full" implies O[buf(u)] has been read out, and "O(u-2) full" (awaited by fold) implies P[buf(u)] is free.
     {
+      const int g = warp == 1 ? 0 : 1;
       const uint32_t idesc_s = instr_desc(128, 64), idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
       const uint32_t hi_k = (128u >> 4) | (1u << 14);              // K-major tiles: SBO = 128 B
       const uint32_t lo_k = 128u << 16;                            //   128-row tiles: LBO = 128 rows * 16 B
-      const uint32_t lo_p = 128u << 16;                            //   P half tile is 128 rows too
       const uint32_t hi_v = ((128u * 16) >> 4) | (1u << 14);       // V as MN-major: SBO = 2048 B (next 8 columns)
       const uint32_t lo_v = (128u >> 4) << 16;                     //                LBO = 128 B (next 8 kv rows)
       const uint32_t q16 = (sbase + off_q) >> 4, kv16 = (sbase + off_kv) >> 4, p16 = (sbase + off_p) >> 4;
       const uint32_t tile16 = tile_bytes >> 4, pt16 = p_bytes >> 4;
       uint32_t kslot = 0, kph = 0;
-      uint32_t qph = 0, sph = 0, pph = 0, oph = 0;   // phase bits indexed [g*2 + buf]
-      uint32_t us[2] = {0, 0};                       // per-group running unit counter on the S-issue side
-      uint32_t up[2] = {0, 0};                       // ... and on the P.V side
-      auto issue_s = [&](int g, int b, uint32_t slot, int half, bool last_of_item) {
-        const int si = g * 2 + (int)(us[g] & 1);
-        ++us[g];
-        mbar_wait(BAR(S_EMPTY + si), ((sph >> si) & 1) ^ 1);
-        sph ^= 1u << si;
+      uint32_t qph = 0, sph = 0, pph = 0;   // phase bits indexed by buffer
+      uint32_t us = 0, up = 0;              // running unit counters (S-issue side, P.V side)
+      auto issue_s = [&](int b, uint32_t slot, int half, bool last_of_item) {
+        const int buf = (int)(us & 1), si = g * 2 + buf;
+        ++us;
+        mbar_wait(BAR(S_EMPTY + si), ((sph >> buf) & 1) ^ 1);
+        sph ^= 1u << buf;
         tc_fence_after();
         const uint32_t qa = q16 + (g * 2 + b) * tile16, kb = kv16 + slot * 2 * tile16 + half * 64;
         if (elect_one()) {
@@ -137,24 +138,44 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
         }
         __syncwarp();
       };
-      auto wait_q = [&](int g, int b) {
-        const int qi = g * 2 + b;
-        mbar_wait(BAR(Q_FULL + qi), (qph >> qi) & 1);
-        qph ^= 1u << qi;
+      auto wait_q = [&](int b) {
+        mbar_wait(BAR(Q_FULL + g * 2 + b), (qph >> b) & 1);
+        qph ^= 1u << b;
+      };
+      auto release_kv = [&]() {
+        if (elect_one()) mma_commit(BAR(KV_EMPTY + kslot));
+        __syncwarp();
+        if (++kslot == ATT_STAGES) { kslot = 0; kph ^= 1; }
       };
       int n_local = 0;
-      if ((int)blockIdx.x < p.n_items) {   // prologue: S of the very first unit
-        const int nq = min(2, NTL - 2 * ((int)blockIdx.x % p.NP));
-        for (int g = 0; g < nq; ++g) wait_q(g, 0);
+      if ((int)blockIdx.x < p.n_items && g < min(2, NTL - 2 * ((int)blockIdx.x % p.NP))) {   // S of the very first unit
+        wait_q(0);
         mbar_wait(BAR(KV_FULL + kslot), kph);
         tc_fence_after();
-        for (int g = 0; g < nq; ++g) issue_s(g, 0, kslot, 0, NU == 1);
+        issue_s(0, kslot, 0, NU == 1);
       }
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
-        const int nq = min(2, NTL - 2 * (item % p.NP));
+        const bool active = g < min(2, NTL - 2 * (item % p.NP));
         const int b = n_local & 1;
         const int next = item + gridDim.x;
-        const int nq_next = next < p.n_items ? min(2, NTL - 2 * (next % p.NP)) : 0;
+        const bool next_active = next < p.n_items && g < min(2, NTL - 2 * (next % p.NP));
+        if (!active) {
+          // this group has no query tile in the item: keep the K/V ring protocol alive (the stage barriers expect
+          // one release from each MMA warp) and pre-issue S for the next item after the last stage
+          for (int j = 0; j < NTL; ++j) {
+            mbar_wait(BAR(KV_FULL + kslot), kph);
+            if (j + 1 == NTL && next_active) {
+              uint32_t nslot = kslot + 1, nph = kph;
+              if (nslot == ATT_STAGES) { nslot = 0; nph ^= 1; }
+              wait_q(b ^ 1);
+              mbar_wait(BAR(KV_FULL + nslot), nph);
+              tc_fence_after();
+              issue_s(b ^ 1, nslot, 0, NU == 1);
+            }
+            release_kv();
+          }
+          continue;
+        }
         for (int u = 0; u < NU; ++u) {
           const int half = u & 1;
           uint32_t nslot = kslot + 1, nph = kph;
@@ -162,48 +183,39 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
           // ---- S for the next unit ----
           if (u + 1 < NU) {
             if (half == 1) { mbar_wait(BAR(KV_FULL + nslot), nph); tc_fence_after(); }
-            for (int g = 0; g < nq; ++g) issue_s(g, b, half == 1 ? nslot : kslot, half ^ 1, u + 2 == NU);
-          } else if (nq_next > 0) {
-            for (int g = 0; g < nq_next; ++g) wait_q(g, b ^ 1);
+            issue_s(b, half == 1 ? nslot : kslot, half ^ 1, u + 2 == NU);
+          } else if (next_active) {
+            wait_q(b ^ 1);
             mbar_wait(BAR(KV_FULL + nslot), nph);
             tc_fence_after();
-            for (int g = 0; g < nq_next; ++g) issue_s(g, b ^ 1, nslot, 0, NU == 1);
+            issue_s(b ^ 1, nslot, 0, NU == 1);
           }
           // ---- O_u = P_u . V[64 keys of this unit] ----
-          for (int g = 0; g < nq; ++g) {
-            const int bi = g * 2 + (int)(up[g] & 1);
-            ++up[g];
-            mbar_wait(BAR(P_FULL + bi), (pph >> bi) & 1);
-            pph ^= 1u << bi;
-            mbar_wait(BAR(O_EMPTY + bi), ((oph >> bi) & 1) ^ 1);
-            oph ^= 1u << bi;
-            tc_fence_after();
-            const uint32_t pa = p16 + bi * pt16, vb = kv16 + kslot * 2 * tile16 + tile16 + half * 64;
-            if (elect_one()) {
+          const int buf = (int)(up & 1), bi = g * 2 + buf;
+          ++up;
+          mbar_wait(BAR(P_FULL + bi), (pph >> buf) & 1);
+          pph ^= 1u << buf;
+          tc_fence_after();
+          const uint32_t pa = p16 + bi * pt16, vb = kv16 + kslot * 2 * tile16 + tile16 + half * 64;
+          if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                mma_lohi(tmem + o_col0 + bi * HDP, (pa + kk * 2 * 128) | lo_p, hi_k, (vb + kk * 16) | lo_v, hi_v, idesc_pv,
-                         (uint32_t)kk);
-              mma_commit(BAR(O_FULL + bi));
-              mma_commit(BAR(P_EMPTY + bi));
-            }
-            __syncwarp();
+            for (int kk = 0; kk < 4; ++kk)
+              mma_lohi(tmem + o_col0 + bi * HDP, (pa + kk * 2 * 128) | lo_k, hi_k, (vb + kk * 16) | lo_v, hi_v, idesc_pv,
+                       (uint32_t)kk);
+            mma_commit(BAR(O_FULL + bi));
           }
-          if (half == 1 || u + 1 == NU) {          // both halves of this K/V stage consumed
-            if (elect_one()) mma_commit(BAR(KV_EMPTY + kslot));
-            __syncwarp();
-            kslot = nslot; kph = nph;
-          }
+          __syncwarp();
+          if (half == 1 || u + 1 == NU) release_kv();   // both halves of this K/V stage consumed by this group
         }
       }
     }
   } else {
     // ===================== softmax groups =====================
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 2;              // warps 2-5: group 0, warps 6-9: group 1
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t sph = 0, pph = 0, oph = 0;         // phase bits per buffer (bit = buf)
+    uint32_t sph = 0, oph = 0;                  // phase bits per buffer (bit = buf)
     uint32_t uc = 0;                            // running unit counter of this group
     const int OC = HDP / 8;                     // 16-byte chunks per output row and head
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -224,8 +236,6 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
         tmem_ld16(lane_addr + o_col0 + bi * HDP, r);
         if (HDP > 16) tmem_ld16(lane_addr + o_col0 + bi * HDP + 16, r + 16);
         tc_wait_ld();
-        tc_fence_before();
-        mbar_arrive(BAR(O_EMPTY + bi));
 #pragma unroll
         for (int e = 0; e < 32; ++e) if (e < HDP) o[e] += __uint_as_float(r[e]);
       };
@@ -255,8 +265,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
         const float alpha = fast_exp2(m_run - mx);
         m_run = mx;
         float rs0 = 0.f, rs1 = 0.f;
-        mbar_wait(BAR(P_EMPTY + bi), ((pph >> buf) & 1) ^ 1);   // P.V two units ago has consumed this P buffer
-        pph ^= 1u << buf;
+        // P[buf] is free: fold() of the previous iteration waited for P.V(u-2), the last reader of this buffer
         uint8_t* pt = smem + off_p + (size_t)bi * p_bytes;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(AttnTcParams p) {
           *reinterpret_cast<uint4*>(pt + ((size_t)c * 128 + m) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         fence_proxy_async();
+        tc_fence_before();
         mbar_arrive(BAR(P_FULL + bi));
         if (u > 0) fold(buf ^ 1);
         l_run = l_run * alpha + (rs0 + rs1);

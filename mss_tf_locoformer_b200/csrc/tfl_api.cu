@@ -375,7 +375,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       smem_set[1] = smem;
     }
     const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
-    attn_tc_kernel<<<grid, 320, smem, st>>>(ap);
+    attn_tc_kernel<<<grid, 352, smem, st>>>(ap);
     TFL_LAUNCH_CHECK();
   }
   {
