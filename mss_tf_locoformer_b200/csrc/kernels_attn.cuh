@@ -356,7 +356,10 @@ __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* 
   }
 }
 
-__global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
+constexpr int QKV_PRODUCER_WARPS = 8;
+constexpr int QKV_THREADS = 32 * (2 + QKV_PRODUCER_WARPS + 8);
+
+__global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -366,13 +369,14 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
   const uint32_t sbase = smem_u32(smem);
   auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
   const int W_FULL = 0, A_FULL = 1, A_EMPTY = 4, D_FULL = 7, D_EMPTY = 10;   // A: 3 slots, D: 3 parts
+  constexpr int NPROD = QKV_PRODUCER_WARPS * 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 16);
   float* tab_gamma = reinterpret_cast<float*>(smem + off_tab);
   for (int i = threadIdx.x; i < C; i += blockDim.x) tab_gamma[i] = p.gamma[i];
   if (threadIdx.x == 0) {
     mbar_init(BAR(W_FULL), 1);
     for (int i = 0; i < 3; ++i) {
-      mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(A_EMPTY + i), 1);
+      mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1);
       mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 256);
     }
     fence_barrier_init();
@@ -415,7 +419,9 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
         if (++slot == 3) { slot = 0; aph ^= 1; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + QKV_PRODUCER_WARPS) {
+    // ---- producers: one (row, group) item per thread and pass; the row stays in registers between the
+    //      sum-of-squares and the scaling, so x is read exactly once ----
     const int tp = threadIdx.x - 64;
     const int G = p.G, D = C / G;
     const float rs = rsqrtf((float)D);
@@ -426,28 +432,47 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = tile / NTL, jt = tile - s * NTL;
       const long long base = p.map.base(s);
-      for (int item = tp; item < 128 * G; item += 128) {
+      for (int item = tp; item < 128 * G; item += NPROD) {
         const int row = item / G, grp = item - row * G;
         const int j = jt * 128 + row;
         const bool valid = j < p.L;
         const float* src = p.x + base + (long long)j * p.map.pos_stride + grp * D;
-        float ss = 0.f;
-        if (valid)
-          for (int d = 0; d < D; d += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-          }
-        const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
-        for (int d = 0; d < D; d += 4) {
-          uint2 pk = make_uint2(0u, 0u);
-          const int c0 = grp * D + d;
-          if (valid) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+        if (D == 32) {
+          float4 v[8];
+#pragma unroll
+          for (int d = 0; d < 8; ++d) v[d] = valid ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float ss = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) ss += v[d].x * v[d].x + v[d].y * v[d].y + v[d].z * v[d].z + v[d].w * v[d].w;
+          const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            const int c0 = grp * 32 + 4 * d;
             const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
-            pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
-            pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
+            uint2 pk;
+            pk.x = pack_bf16(v[d].x * inv * gm.x, v[d].y * inv * gm.y);
+            pk.y = pack_bf16(v[d].z * inv * gm.z, v[d].w * inv * gm.w);
+            *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
           }
-          *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
+        } else {
+          float ss = 0.f;
+          if (valid)
+            for (int d = 0; d < D; d += 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+              ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+          const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+          for (int d = 0; d < D; d += 4) {
+            uint2 pk = make_uint2(0u, 0u);
+            const int c0 = grp * D + d;
+            if (valid) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+              const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+              pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
+              pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
+            }
+            *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
+          }
         }
       }
       fence_proxy_async();
@@ -455,7 +480,8 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
       if (++slot == 3) { slot = 0; ph ^= 1; }
     }
   } else {
-    const int e = (warp - 6) >> 2;             // column half owned by this group
+    const int ew = warp - (2 + QKV_PRODUCER_WARPS);
+    const int e = ew >> 2;                     // column half owned by this group
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -466,7 +492,11 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = tile / NTL, jt = tile - s * NTL;
       const int j = min(jt * 128 + m, p.L - 1);
-      const float2* rt = p.rope != nullptr ? p.rope + (size_t)j * halfp : nullptr;
+      // RoPE factors of this row: shared by q and k and by all heads -> registers, loaded once per tile
+      float2 cs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)j * halfp + i]) : make_float2(1.f, 0.f);
       for (int part = 0; part < 3; ++part) {
         mbar_wait(BAR(D_FULL + part), (uint32_t)(it & 1));
         tc_fence_after();
@@ -479,9 +509,9 @@ __global__ void __launch_bounds__(448, 1) qkv_tc_kernel(QkvTcParams p) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
-            if (part < 2 && rt != nullptr) {
-              const float2 cs = __ldg(&rt[(d0 + i) >> 1]);
-              const float ra = a * cs.x - b * cs.y, rb = b * cs.x + a * cs.y;
+            if (part < 2) {
+              const float2 f = d0 == 0 ? cs[i >> 1] : cs[8 + (i >> 1)];   // d0 is 0 or 16 (HDP <= 32)
+              const float ra = a * f.x - b * f.y, rb = b * f.x + a * f.y;
               a = ra; b = rb;
             }
             if (part == 0) { a *= p.qscale; b *= p.qscale; }

@@ -362,7 +362,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       smem_set[0] = smem;
     }
     const int grid = q.n_tiles < pl->sm_count ? q.n_tiles : pl->sm_count;
-    qkv_tc_kernel<<<grid, 448, smem, st>>>(q);
+    qkv_tc_kernel<<<grid, QKV_THREADS, smem, st>>>(q);
     TFL_LAUNCH_CHECK();
   }
   {
