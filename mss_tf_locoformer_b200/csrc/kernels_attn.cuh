@@ -437,22 +437,25 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
         const int j = jt * 128 + row;
         const bool valid = j < p.L;
         const float* src = p.x + base + (long long)j * p.map.pos_stride + grp * D;
-        if (D == 32) {
+        if (D <= 32) {
           float4 v[8];
 #pragma unroll
-          for (int d = 0; d < 8; ++d) v[d] = valid ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int d = 0; d < 8; ++d)
+            v[d] = (valid && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
           float ss = 0.f;
 #pragma unroll
           for (int d = 0; d < 8; ++d) ss += v[d].x * v[d].x + v[d].y * v[d].y + v[d].z * v[d].z + v[d].w * v[d].w;
           const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
 #pragma unroll
           for (int d = 0; d < 8; ++d) {
-            const int c0 = grp * 32 + 4 * d;
-            const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
-            uint2 pk;
-            pk.x = pack_bf16(v[d].x * inv * gm.x, v[d].y * inv * gm.y);
-            pk.y = pack_bf16(v[d].z * inv * gm.z, v[d].w * inv * gm.w);
-            *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
+            if (4 * d < D) {
+              const int c0 = grp * D + 4 * d;
+              const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+              uint2 pk;
+              pk.x = pack_bf16(v[d].x * inv * gm.x, v[d].y * inv * gm.y);
+              pk.y = pack_bf16(v[d].z * inv * gm.z, v[d].w * inv * gm.w);
+              *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
+            }
           }
         } else {
           float ss = 0.f;

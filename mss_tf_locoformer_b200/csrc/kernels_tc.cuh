@@ -24,6 +24,9 @@ namespace tfl {
 
 constexpr int TC_HC = 64;             // hidden channels per chunk (D1 tile = 2*HC TMEM columns)
 constexpr int TC_SMEM_MAX = 232448;   // 227 KB opt-in shared memory per CTA
+#ifndef TC_A_EXTRA
+#define TC_A_EXTRA 2                  // A-tile slots beyond the NT tiles being multiplied (prefetch depth)
+#endif
 
 struct FfnTcGeom {
   int C, H, KT, G, NT, NS;            // NS = weight ring stages
@@ -49,7 +52,7 @@ inline bool ffn_tc_geometry(int C, int H, int KT, int G, FfnTcGeom* g) {
   g->a_slot_bytes = (uint32_t)(C / 8) * g->AR * 16;
   g->g_buf_bytes = (uint32_t)(TC_HC / 8) * g->AR * 16;
   uint32_t off = 0;
-  g->off_a = off; off += (g->NT + 1) * g->a_slot_bytes;
+  g->off_a = off; off += (g->NT + TC_A_EXTRA) * g->a_slot_bytes;
   g->off_g = off; off += g->NT * g->g_buf_bytes;
   g->off_tab = off; off += (2 * H + 2 * C) * 4;
   off = (off + 15) & ~15u;
@@ -158,17 +161,17 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = g.C, H = g.H, KT = g.KT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS, NS = g.NS;
   const int KH = g.KH, TPS = g.TPS;
-  constexpr int NA = NT + 1;
+  constexpr int NA = NT + TC_A_EXTRA;
   const uint32_t sbase = smem_u32(smem);
   float* tab_b1 = reinterpret_cast<float*>(smem + g.off_tab);
   float* tab_b2 = tab_b1 + 2 * H;
   float* tab_gamma = tab_b2 + C;
   const uint32_t bar0 = sbase + g.off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  // barrier map: 0..7 w_full, 8..15 w_empty, 16..18 a_full, 19..21 a_empty, 22..23 d1_full[tile], 24..25 d1_empty,
-  // 26..27 g_full, 28..29 g_empty, 30..31 d2_full, 32..33 d2_empty; slot 48: TMEM base address
-  const int W_FULL = 0, W_EMPTY = 8, A_FULL = 16, A_EMPTY = 19, D1_FULL = 22, D1_EMPTY = 24, G_FULL = 26, G_EMPTY = 28,
-            D2_FULL = 30, D2_EMPTY = 32;
+  // barrier map: 0..7 w_full, 8..15 w_empty, 16..19 a_full, 20..23 a_empty, 24..25 d1_full[tile], 26..27 d1_empty,
+  // 28..29 g_full, 30..31 g_empty, 32..33 d2_full, 34..35 d2_empty; slot 48: TMEM base address
+  const int W_FULL = 0, W_EMPTY = 8, A_FULL = 16, A_EMPTY = 20, D1_FULL = 24, D1_EMPTY = 26, G_FULL = 28, G_EMPTY = 30,
+            D2_FULL = 32, D2_EMPTY = 34;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bar + 8 * 48);
 
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) tab_b1[i] = p.b1[i];
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(A_EMPTY + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(A_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(D1_FULL + i), 1); mbar_init(BAR(D1_EMPTY + i), 128);
       mbar_init(BAR(G_FULL + i), 128); mbar_init(BAR(G_EMPTY + i), 1);
@@ -313,12 +316,17 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
       }
     }
   } else if (warp < 6) {
-    // ===================== A producers: x -> RMSGroupNorm -> bf16 chunk-major tile =====================
+    // ===================== A producers / output writers =====================
+    // x -> RMSGroupNorm -> bf16 chunk-major A tile for the NEXT tile pair, then the final epilogue of the current
+    // pair (transposed-conv accumulator + bias + residual -> y), so the SwiGLU warps never leave the chunk loop.
     const int tp = threadIdx.x - 64;  // 0..127
     const int G = g.G, D = C / G;
     const float rs = rsqrtf((float)D);
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;       // tile row in the final epilogue
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t slot = 0, ph = 0;
-    for (int it = 0; it < n_iter; ++it)
+    auto produce = [&](int it) {
       _Pragma("unroll") for (int t = 0; t < NT; ++t) {
         mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
         uint8_t* at = smem + g.off_a + (size_t)slot * g.a_slot_bytes;
@@ -334,75 +342,58 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
             valid = j >= KT - 1;
             if (valid) src = p.x + p.map.base(s) + (long long)(j - (KT - 1)) * p.map.pos_stride + grp * D;
           }
-          float ss = 0.f;
-          if (valid)
+          if (D <= 32) {
+            // the whole group (<= 32 channels) is fetched with back-to-back independent 128-bit loads and stays in
+            // registers between the sum of squares and the scaling: one memory latency per item, x read once
+            float4 v[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+              v[d] = (valid && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float ss = 0.f;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) ss += v[d].x * v[d].x + v[d].y * v[d].y + v[d].z * v[d].z + v[d].w * v[d].w;
+            const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+              if (4 * d < D) {
+                const int c0 = grp * D + 4 * d;
+                const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+                uint2 pk;
+                pk.x = pack_bf16(v[d].x * inv * gm.x, v[d].y * inv * gm.y);
+                pk.y = pack_bf16(v[d].z * inv * gm.z, v[d].w * inv * gm.w);
+                *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * AR + row) * 16 + (c0 & 7) * 2) = pk;
+              }
+            }
+          } else {
+            float ss = 0.f;
+            if (valid)
+              for (int d = 0; d < D; d += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+              }
+            const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
             for (int d = 0; d < D; d += 4) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
-              ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+              uint2 pk = make_uint2(0u, 0u);
+              const int c0 = grp * D + d;
+              if (valid) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));  // L1 hit
+                const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+                pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
+                pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
+              }
+              *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * AR + row) * 16 + (c0 & 7) * 2) = pk;
             }
-          const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
-          for (int d = 0; d < D; d += 4) {
-            uint2 pk = make_uint2(0u, 0u);
-            const int c0 = grp * D + d;
-            if (valid) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));  // L1 hit
-              const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
-              pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
-              pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
-            }
-            *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * AR + row) * 16 + (c0 & 7) * 2) = pk;
           }
         }
         fence_proxy_async();
         mbar_arrive(BAR(A_FULL + slot));
         if (++slot == (uint32_t)NA) { slot = 0; ph ^= 1; }
       }
-  } else {
-    // ===================== epilogue groups (one per tile slot) =====================
-    const int t = (warp - 6) >> 2;
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int m = quarter * 32 + lane;       // tile row
-    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* gt = smem + g.off_g + (size_t)t * g.g_buf_bytes;
-    uint32_t qpar = 0;
+    };
+    produce(0);
     for (int it = 0; it < n_iter; ++it) {
-      for (int c = 0; c < NC; ++c) {
-        mbar_wait(BAR(D1_FULL + t), qpar);
-        tc_fence_after();
-        uint32_t packed[TC_HC / 2];
-        const float* bv = tab_b1 + c * TC_HC;
-        const float* bg = tab_b1 + H + c * TC_HC;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t rv[32], rg[32];
-          tmem_ld32(lane_addr + t * (2 * TC_HC) + half * 32, rv);
-          tmem_ld32(lane_addr + t * (2 * TC_HC) + TC_HC + half * 32, rg);
-          tc_wait_ld();
-          if (half == 1) {  // D1 fully read: hand it back to the MMA thread before the math
-            tc_fence_before();
-            mbar_arrive(BAR(D1_EMPTY + t));
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float hv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float val = __uint_as_float(rv[i + u]) + bv[half * 32 + i + u];
-              const float gate = __uint_as_float(rg[i + u]) + bg[half * 32 + i + u];
-              hv[u] = swiglu_fast(val, gate);                         // value * SiLU(gate), :648-649
-            }
-            packed[half * 16 + (i >> 1)] = pack_bf16(hv[0], hv[1]);
-          }
-        }
-        mbar_wait(BAR(G_EMPTY + t), qpar ^ 1);   // transposed-conv MMAs of the previous chunk are done with G
-#pragma unroll
-        for (int ch = 0; ch < TC_HC / 8; ++ch)
-          *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
-              make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-        fence_proxy_async();
-        mbar_arrive(BAR(G_FULL + t));
-        qpar ^= 1;
-      }
+      if (it + 1 < n_iter) produce(it + 1);
+      _Pragma("unroll") for (int t = 0; t < NT; ++t) {
       // ---- final: transposed-conv accumulator + bias + residual -> y ----
       mbar_wait(BAR(D2_FULL + t), (uint32_t)(it & 1));
       tc_fence_after();
@@ -457,6 +448,54 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
       }
       tc_fence_before();
       mbar_arrive(BAR(D2_EMPTY + t));
+      }
+    }
+  } else {
+    // ===================== epilogue groups (one per tile slot) =====================
+    const int t = (warp - 6) >> 2;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;       // tile row
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* gt = smem + g.off_g + (size_t)t * g.g_buf_bytes;
+    uint32_t qpar = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      for (int c = 0; c < NC; ++c) {
+        mbar_wait(BAR(D1_FULL + t), qpar);
+        tc_fence_after();
+        uint32_t packed[TC_HC / 2];
+        const float* bv = tab_b1 + c * TC_HC;
+        const float* bg = tab_b1 + H + c * TC_HC;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(lane_addr + t * (2 * TC_HC) + half * 32, rv);
+          tmem_ld32(lane_addr + t * (2 * TC_HC) + TC_HC + half * 32, rg);
+          tc_wait_ld();
+          if (half == 1) {  // D1 fully read: hand it back to the MMA thread before the math
+            tc_fence_before();
+            mbar_arrive(BAR(D1_EMPTY + t));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float hv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float val = __uint_as_float(rv[i + u]) + bv[half * 32 + i + u];
+              const float gate = __uint_as_float(rg[i + u]) + bg[half * 32 + i + u];
+              hv[u] = swiglu_fast(val, gate);                         // value * SiLU(gate), :648-649
+            }
+            packed[half * 16 + (i >> 1)] = pack_bf16(hv[0], hv[1]);
+          }
+        }
+        mbar_wait(BAR(G_EMPTY + t), qpar ^ 1);   // transposed-conv MMAs of the previous chunk are done with G
+#pragma unroll
+        for (int ch = 0; ch < TC_HC / 8; ++ch)
+          *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
+              make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+        fence_proxy_async();
+        mbar_arrive(BAR(G_FULL + t));
+        qpar ^= 1;
+      }
     }
   }
   tc_fence_before();
