@@ -115,6 +115,14 @@ int tfl_separator_forward(const tfl_plan* plan, const void* packed, const float*
 int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, int seg_index0,
                     int n_seg_total, float* track, int64_t n_track, tfl_stream_t stream);
 
+/* Diagnostic: every mbarrier wait in the tcgen05 kernels is bounded.  out5 = {timed_out, block, thread, shared-memory
+ * address of the barrier, parity} of the first wait that expired since the last reset (device synchronising call). */
+int tfl_debug_timeout(uint32_t* out5, int reset);
+
+/* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN
+ * kernel records clock64() stamps of its pipeline events ([event * 64 + chunk index]). */
+int tfl_debug_set_trace(void* device_buffer);
+
 /* Diagnostic: exercises the tcgen05 plumbing of the bf16 path on one 128-row tile.
  * mode 0: D[128, N] = sum_{tap < taps} A[m + tap, :] . B[tap][n, :]   A [128 + taps - 1, Kd], B [taps, N, Kd]
  * mode 1: D[128, N] = A[m, :] . B[:, n]                               A [128, Kd], B [Kd, N] (N-contiguous)

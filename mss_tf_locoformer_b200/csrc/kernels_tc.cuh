@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  unsigned long long* const tr = (blockIdx.x == 0 && lane == 0) ? g_trace : nullptr;   // diagnostic event trace
   const int n_pairs = (p.n_tiles + NT - 1) / NT;
   const int n_iter = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int stages_per_iter = NC * (KT * KH + KS);
@@ -239,7 +240,9 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
       uint32_t qpar = 0;                                   // parity of the running chunk counter
       for (int it = 0; it < n_iter; ++it) {
         auto mma2 = [&](int cc, uint32_t par) {
+          trace_event(tr, 7, it * NC + cc);
           _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(G_FULL + t), par);
+          trace_event(tr, 8, it * NC + cc);
           if (cc == 0) _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(D2_EMPTY + t), (uint32_t)((it & 1) ^ 1));
           tc_fence_after();
           for (int s = 0; s < KS; ++s) {
@@ -269,13 +272,16 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
             _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(G_EMPTY + t));
           }
           __syncwarp();
+          trace_event(tr, 9, it * NC + cc);
         };
         for (int c = 0; c < NC; ++c) {
+          trace_event(tr, 0, it * NC + c);
           _Pragma("unroll") for (int t = 0; t < NT; ++t) {
             if (c == 0) mbar_wait(BAR(A_FULL + aslot[t]), aph[t]);
             mbar_wait(BAR(D1_EMPTY + t), qpar ^ 1);
           }
           tc_fence_after();
+          trace_event(tr, 1, it * NC + c);
           for (int k = 0; k < KT; ++k)
             for (int hf = 0; hf < KH; ++hf) {
               mbar_wait(BAR(W_FULL + wslot), wph);
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
               _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(A_EMPTY + aslot[t]));
           }
           __syncwarp();
+          trace_event(tr, 2, it * NC + c);
           if (c > 0) mma2(c - 1, qpar ^ 1);
           qpar ^= 1;
         }
@@ -460,8 +467,10 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
     uint32_t qpar = 0;
     for (int it = 0; it < n_iter; ++it) {
       for (int c = 0; c < NC; ++c) {
+        unsigned long long* const etr = warp == 6 ? tr : nullptr;
         mbar_wait(BAR(D1_FULL + t), qpar);
         tc_fence_after();
+        trace_event(etr, 3, it * NC + c);
         uint32_t packed[TC_HC / 2];
         const float* bv = tab_b1 + c * TC_HC;
         const float* bg = tab_b1 + H + c * TC_HC;
@@ -474,6 +483,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
           if (half == 1) {  // D1 fully read: hand it back to the MMA thread before the math
             tc_fence_before();
             mbar_arrive(BAR(D1_EMPTY + t));
+            trace_event(etr, 4, it * NC + c);
           }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -487,13 +497,16 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
             packed[half * 16 + (i >> 1)] = pack_bf16(hv[0], hv[1]);
           }
         }
+        trace_event(etr, 10, it * NC + c);
         mbar_wait(BAR(G_EMPTY + t), qpar ^ 1);   // transposed-conv MMAs of the previous chunk are done with G
+        trace_event(etr, 5, it * NC + c);
 #pragma unroll
         for (int ch = 0; ch < TC_HC / 8; ++ch)
           *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
               make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
         fence_proxy_async();
         mbar_arrive(BAR(G_FULL + t));
+        trace_event(etr, 6, it * NC + c);
         qpar ^= 1;
       }
     }

@@ -57,17 +57,42 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must never hang the GPU.  The first wait that times out records
+// (block, thread, barrier address, parity) in g_wait_timeout and raises an abort flag; every later wait returns
+// at once, so the kernel drains (with garbage results) and the host reports the error (tfl_debug_timeout).
+__device__ unsigned int g_wait_timeout[5] = {0, 0, 0, 0, 0};
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("tfl: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (*(volatile unsigned int*)&g_wait_timeout[0] != 0) return;
+    if (clock64() - t0 > 1000000000LL) {
+      if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
+        g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
+        __threadfence();
+      }
+      return;
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // fast path: a handful of polls inline (try_wait itself suspends the thread for a HW-defined time slice)
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
+
+// Optional event trace (diagnostic): when tfl_debug_set_trace() has installed a buffer, block 0 of the traced kernels
+// stores clock64() stamps at [event * 64 + index].
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_event(unsigned long long* tr, int event, int index) {
+  if (tr != nullptr && index >= 0 && index < 64) tr[event * 64 + index] = (unsigned long long)clock64();
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / bulk copy reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -618,6 +618,22 @@ int tfl_segment_ola(const float* seg_audio, int n_src, int B, int seg_len, int s
   return 0;
 }
 
+int tfl_debug_set_trace(void* device_buffer) {
+  unsigned long long* ptr = (unsigned long long*)device_buffer;
+  TFL_CUDA(cudaMemcpyToSymbol(tc::g_trace, &ptr, sizeof(ptr)));
+  return 0;
+}
+
+int tfl_debug_timeout(uint32_t* out5, int reset) {
+  TFL_CHECK(out5 != nullptr, "null argument");
+  TFL_CUDA(cudaMemcpyFromSymbol(out5, tc::g_wait_timeout, 5 * sizeof(uint32_t)));
+  if (reset) {
+    const uint32_t zero[5] = {0, 0, 0, 0, 0};
+    TFL_CUDA(cudaMemcpyToSymbol(tc::g_wait_timeout, zero, sizeof(zero)));
+  }
+  return 0;
+}
+
 int tfl_tc_selftest(const float* A, const float* B, float* D, void* scratch, int N, int Kd, int taps, int mode,
                     tfl_stream_t stream) {
   TFL_CHECK(A && B && D && scratch, "null argument");

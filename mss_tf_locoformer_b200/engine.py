@@ -247,3 +247,11 @@ def tc_selftest(A: torch.Tensor, B: torch.Tensor, taps: int, mode: int) -> torch
         check(lib.tfl_tc_selftest(A.contiguous().data_ptr(), B.contiguous().data_ptr(), D.data_ptr(),
                                   scratch.data_ptr(), N, Kd, taps, mode, _stream()))
     return D
+
+
+def debug_timeout(reset: bool = True):
+    """(timed_out, block, thread, barrier smem address, parity) of the first expired mbarrier wait (tfl_debug_timeout)."""
+    lib = _lib.load()
+    out = (C.c_uint32 * 5)()
+    check(lib.tfl_debug_timeout(out, 1 if reset else 0))
+    return tuple(int(v) for v in out)
