@@ -119,6 +119,18 @@ int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, i
  * address of the barrier, parity} of the first wait that expired since the last reset (device synchronising call). */
 int tfl_debug_timeout(uint32_t* out5, int reset);
 
+/* BandSplitModule.band_split, standalone/bslocoformer_separator.py:241-254.  spec [B, M, T, F, 2] -> x [B, T, nb, C].
+ * `weights` is one fp32 buffer, `table` (device int64, 16 entries per band) its index:
+ *   [0] first bin  [1] width  [2] gn.weight  [3] gn.bias  [4] conv.weight^T [K][C]  [5] conv.bias            (split)
+ *   [6] gn.weight  [7] gn.bias  [8] W1^T [C][4C]  [9] b1  [10] W3^T [4C][4C]  [11] b3  [12] W4^T [4C][O]  [13] b4  (decode) */
+int tfl_bs_band_split(const float* spec, int batch, int n_chan, int n_frames, int n_freq, int emb_dim, int n_bands,
+                      int max_width, const int64_t* table, const float* weights, float* x, tfl_stream_t stream);
+/* BandSplitModule.bandwise_decoding + complex mask, :256-270 and :175-182.
+ * x [B, T, nb, C], spec [B, M, T, F, 2] -> est [B, S, M, T, F, 2] (= spec * mask when masking != 0). */
+int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan, int n_frames, int n_freq, int emb_dim,
+                       int n_bands, int n_src, const int64_t* table, const float* weights, float* est, int masking,
+                       tfl_stream_t stream);
+
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN
  * kernel records clock64() stamps of its pipeline events ([event * 64 + chunk index]). */
 int tfl_debug_set_trace(void* device_buffer);

@@ -6,11 +6,11 @@ every arithmetic step runs in the hand-written CUDA kernels of ``csrc/`` behind 
 declared in ``include/tfl.h``.  No CPU path, no Triton, no multi-backend dispatch: importing
 works anywhere, running needs the built library and a CUDA device.
 """
-from .models import TFLocoformerMSS, TFLocoformerSeparator, strip_prefix  # noqa: F401
+from .models import BSLocoformerSeparator, TFLocoformerMSS, TFLocoformerSeparator, strip_prefix  # noqa: F401
 from .modules import (  # noqa: F401
     ConvDeconv1d, LocoformerBlock, MSSTransform, MultiHeadSelfAttention, RMSGroupNorm, RotaryEmbedding,
     SwiGLUConvDeconv1d, TFLocoformerBlock,
 )
 from .engine import Engine, segment_ola  # noqa: F401
 
-__all__ = ["TFLocoformerMSS", "TFLocoformerSeparator", "strip_prefix", "Engine", "segment_ola"]
+__all__ = ["TFLocoformerMSS", "TFLocoformerSeparator", "BSLocoformerSeparator", "strip_prefix", "Engine", "segment_ola"]

@@ -40,6 +40,8 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),
     "tfl_separator_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _I, _P]),
     "tfl_segment_ola": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "tfl_bs_band_split": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "tfl_bs_band_decode": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "tfl_debug_set_trace": (_I, [_P]),
     "tfl_debug_timeout": (_I, [C.POINTER(C.c_uint32), _I]),
     "tfl_tc_selftest": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

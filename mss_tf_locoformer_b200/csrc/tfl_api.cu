@@ -9,6 +9,7 @@
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_attn.cuh"
+#include "kernels_bs.cuh"
 
 namespace tfl {
 
@@ -614,6 +615,40 @@ int tfl_segment_ola(const float* seg_audio, int n_src, int B, int seg_len, int s
   dim3 grid((seg_len + 255) / 256 < 296 ? (seg_len + 255) / 256 : 296, B, n_src);
   segment_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seg_audio, n_src, B, seg_len, seg_index0, n_seg_total,
                                                              track, n_track);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_bs_band_split(const float* spec, int B, int M, int T, int F, int C, int nb, int max_width,
+                      const int64_t* table, const float* weights, float* x, tfl_stream_t stream) {
+  TFL_CHECK(spec && table && weights && x, "null argument");
+  TFL_CHECK(B >= 1 && (M == 1 || M == 2) && T >= 1 && F >= 1 && C >= 1 && nb >= 1 && max_width >= 1, "bad band-split shape");
+  const size_t smem = ((size_t)max_width * 2 * M * BS_TT + 64) * sizeof(float);
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TFL_CUDA(cudaFuncSetAttribute(bs_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid(nb, (T + BS_TT - 1) / BS_TT, B);
+  bs_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(spec, M, T, F, C, nb, (const long long*)table, weights, x, 1e-5f);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_bs_band_decode(const float* x, const float* spec, int B, int M, int T, int F, int C, int nb, int n_src,
+                       const int64_t* table, const float* weights, float* est, int masking, tfl_stream_t stream) {
+  TFL_CHECK(x && spec && table && weights && est, "null argument");
+  TFL_CHECK(B >= 1 && (M == 1 || M == 2) && T >= 1 && F >= 1 && C >= 1 && nb >= 1 && n_src >= 1, "bad band-decode shape");
+  const size_t smem = ((size_t)9 * C * BS_TT + 64) * sizeof(float);
+  TFL_CHECK(smem <= (size_t)TC_SMEM_MAX, "emb_dim too large for the band decoder");
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TFL_CUDA(cudaFuncSetAttribute(bs_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid(nb, (T + BS_TT - 1) / BS_TT, B);
+  bs_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, spec, M, T, F, C, nb, n_src, (const long long*)table, weights,
+                                                              est, masking, 1e-5f);
   TFL_LAUNCH_CHECK();
   return 0;
 }

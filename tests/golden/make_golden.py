@@ -152,11 +152,11 @@ if __name__ == "__main__":
              ffn_hidden_dim=[48, 48], conv1d_kernel=8, conv1d_shift=1, dropout=0.0, eps=1e-5),
              (1, 20, 33), seed=7)
     # BS-Locoformer (tests/test_bslocoformer.py): stft 2048 -> 1025 bins, 62 bands; stereo + masking
-    bs_case("bs_stereo_mask", dict(num_spk=2, n_layers=1, emb_dim=8, norm_type="rmsgroupnorm", num_groups=4,
+    bs_case("bs_stereo_mask", dict(num_spk=2, n_layers=1, emb_dim=8, norm_type="rmsgroupnorm", num_groups=2,
             tf_order="ft", n_heads=2, attention_dim=8, pos_enc="rope", ffn_type=mac, ffn_hidden_dim=[16, 16],
             conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5, sample_rate=44100, stft_size=2048,
             masking=True, stereo=True), (1, 2, 5, 1025), seed=8)
-    bs_case("bs_mono_map", dict(num_spk=1, n_layers=1, emb_dim=8, norm_type="rmsgroupnorm", num_groups=4,
+    bs_case("bs_mono_map", dict(num_spk=1, n_layers=1, emb_dim=8, norm_type="rmsgroupnorm", num_groups=2,
             tf_order="ft", n_heads=2, attention_dim=8, pos_enc="rope", ffn_type="swiglu_conv1d",
             ffn_hidden_dim=16, conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5, sample_rate=48000,
             stft_size=2048, masking=False, stereo=False), (1, 4, 1025), seed=9)

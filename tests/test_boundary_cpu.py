@@ -35,6 +35,15 @@ def test_reference_state_dict_loads_strict(name, cls):
     model.load_state_dict(pkg.strip_prefix(prefixed), strict=True)
 
 
+@pytest.mark.parametrize("name", ["bs_stereo_mask", "bs_mono_map"])
+def test_bs_state_dict_loads_strict(name):
+    cfg, sd, _ = load_golden(name)
+    model = pkg.BSLocoformerSeparator(**cfg)
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    assert len(model.band_split_module.bands) == (62 if cfg["sample_rate"] == 44100 else 61)
+
+
 def test_seeded_init_matches_reference_init():
     """Same RNG consumption order as the reference constructor => same random-init weights."""
     cfg, sd, _ = load_golden("sep_nope_k1")

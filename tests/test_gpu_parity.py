@@ -220,3 +220,16 @@ def test_full_track_segments_match_oracle_stitch(pkg):
     assert list(got) == list(want)
     for k in want:
         _check(got[k], want[k], what=f"track/{k}")
+
+
+@pytest.mark.parametrize("name", ["bs_stereo_mask", "bs_mono_map"])
+def test_bs_separator_golden_fp32(pkg, name):
+    """BS-Locoformer (band-split encoder, Locoformer blocks over the band axis, band-wise decoder, complex mask)."""
+    cfg, sd, arr = load_golden(name)
+    model = pkg.BSLocoformerSeparator(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(arr["spec_in"].cuda())
+    assert out.shape == arr["spec_out"].shape
+    _check(out, arr["spec_out"], maxabs=2e-4, what=name)
