@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=8, help="6-s segments per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--track", type=float, default=0.0,
+                    help="BASELINE config 3: separate ONE synthetic track of this many seconds, 6-s segments at 50 %% overlap "
+                         "sharded over the ranks (strong scaling); prints its own JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -227,6 +230,31 @@ def main():
             out_host.copy_(torch.stack([out[k] for k in names]), non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller needs the result on the host
 
+    if args.track > 0:
+        from mss_tf_locoformer_b200.segments import separate_track, segment_starts
+        n_track = int(args.track * SR)
+        track = make_mixture(1, n_track, seed=99)[0].to(dev)
+
+        def step_track():
+            with torch.no_grad():
+                return separate_track(model, track, seg_len=SEG, batch=B)
+
+        for _ in range(max(1, args.warmup // 3)):
+            step_track()
+        ms = timed(step_track, args.steps)
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": args.track * args.steps / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"full-track {args.track:.0f}-s mono, {len(segment_starts(n_track, SEG))} segments of 6 s at "
+                                       f"50 % overlap, sharded over {world} rank(s), NCCL sum-reduce stitch",
+                           "batch_per_gpu": B, "precision": args.precision}}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     for _ in range(args.warmup):
         step_resident()
     n0 = lib.tfl_launch_count()
@@ -249,7 +277,7 @@ def main():
                    "x_realtime_per_gpu": value / world},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": world * mix_host.numel() * 4,
                 "d2h_bytes_per_step": world * out_host.numel() * 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * world,
     }
     if rank == 0:
         line["clocks"] = clocks.summary()

@@ -233,3 +233,39 @@ def test_bs_separator_golden_fp32(pkg, name):
         out = model(arr["spec_in"].cuda())
     assert out.shape == arr["spec_out"].shape
     _check(out, arr["spec_out"], maxabs=2e-4, what=name)
+
+
+def test_full_size_properties_bf16(pkg):
+    """BASELINE configs[1] at full size (Variant D, 6 layers, 6-s segments): properties that need no oracle run."""
+    import bench
+    model = bench.make_state_dict(dict(bench.VARIANT_D)).cuda()
+    model.precision = "bf16"
+    mix = bench.make_mixture(3, bench.SEG).cuda()
+    with torch.no_grad():
+        full = model(mix)
+        again = model(mix)
+        one = model(mix[1:2])
+    for k in full:
+        assert full[k].shape == (3, bench.SEG) and torch.isfinite(full[k]).all()
+        assert torch.equal(full[k], again[k]), k                      # run-to-run deterministic
+        assert torch.equal(full[k][1], one[k][0]), k                  # batch rows independent, bit for bit
+    # STFT -> iSTFT round trip (NOLA) through the same kernels at full size
+    eng = model._ready()
+    spec = eng.stft(mix)
+    est = spec.unsqueeze(1).expand(-1, 4, -1, -1, -1).contiguous()
+    back = eng.istft(est, bench.SEG)
+    n_ok = (bench.SEG // 1024) * 1024 - 2048
+    assert float((back[0][:, :n_ok] - mix[:, :n_ok]).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("n_samples", [129, 130, 255, 256, 257, 1000, 1024, 4097])
+def test_ragged_lengths_fp32(pkg, n_samples):
+    """Edge lengths around the reflect-pad minimum (n_fft/2 + 1) and hop multiples; workspace re-planned per shape."""
+    cfg, sd, arr, model = _mss(pkg, "mss_hop2_macaron")
+    mix = _mixture(n_samples, 1, seed=n_samples)
+    want = oracle.mss_forward(sd, cfg, mix)
+    with torch.no_grad():
+        got = model(mix.cuda())
+    for k in want:
+        assert got[k].shape == (1, n_samples)
+        _check(got[k], want[k], what=f"T={n_samples}/{k}")
