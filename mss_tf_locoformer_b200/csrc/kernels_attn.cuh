@@ -23,7 +23,9 @@ namespace tfl {
 
 struct AttnTcParams {
   const __nv_bfloat16* qkv; __nv_bfloat16* o;
-  int nseq, heads, L, NTL, HDP, NP;   // NP = query-tile pairs per (seq, head)
+  int nseq, heads, L, NTL, HDP, NP;   // NTL = 128-row tiles of the images; NP = query-tile pairs per (seq, head)
+  int NQT;                            // query tiles handled here (the last rows may go to attn_tail_rows_kernel)
+  int NU;                             // 64-key units per sequence (the last one may be partial: masked)
   int n_items;
 };
 
@@ -40,7 +42,8 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HDP = p.HDP, NTL = p.NTL;
-  const int NU = (p.L + 63) / 64;                                 // 64-key units per sequence
+  const int NU = p.NU;                                            // 64-key units per sequence
+  const int NST = (NU + 1) / 2;                                   // K/V ring stages (128-row tiles) per item
   const uint32_t tile_bytes = (uint32_t)HDP * 128 * 2;          // one Q / K / V tile (128 rows)
   const uint32_t p_bytes = 128u * 64 * 2;                        // one P half-tile (128 queries x 64 keys)
   const uint32_t off_q = 0, off_kv = 4 * tile_bytes, off_p = off_kv + ATT_STAGES * 2 * tile_bytes;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
         const int pair = item % p.NP, sh = item / p.NP;            // sh = seq * heads + head
         const __nv_bfloat16* qb = p.qkv + (size_t)sh * NTL * HDP * 128;
-        const int nq = min(2, NTL - 2 * pair);
+        const int nq = min(2, p.NQT - 2 * pair);
         const int b = n_local & 1;
         for (int g = 0; g < nq; ++g) {
           const int qi = g * 2 + b;
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
           }
           __syncwarp();
         }
-        for (int j = 0; j < NTL; ++j) {
+        for (int j = 0; j < NST; ++j) {
           mbar_wait(BAR(KV_EMPTY + kslot), kph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(BAR(KV_FULL + kslot), 2 * tile_bytes);
@@ -148,23 +151,23 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
         if (++kslot == ATT_STAGES) { kslot = 0; kph ^= 1; }
       };
       int n_local = 0;
-      if ((int)blockIdx.x < p.n_items && g < min(2, NTL - 2 * ((int)blockIdx.x % p.NP))) {   // S of the very first unit
+      if ((int)blockIdx.x < p.n_items && g < min(2, p.NQT - 2 * ((int)blockIdx.x % p.NP))) {   // S of the very first unit
         wait_q(0);
         mbar_wait(BAR(KV_FULL + kslot), kph);
         tc_fence_after();
         issue_s(0, kslot, 0, NU == 1);
       }
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
-        const bool active = g < min(2, NTL - 2 * (item % p.NP));
+        const bool active = g < min(2, p.NQT - 2 * (item % p.NP));
         const int b = n_local & 1;
         const int next = item + gridDim.x;
-        const bool next_active = next < p.n_items && g < min(2, NTL - 2 * (next % p.NP));
+        const bool next_active = next < p.n_items && g < min(2, p.NQT - 2 * (next % p.NP));
         if (!active) {
           // this group has no query tile in the item: keep the K/V ring protocol alive (the stage barriers expect
           // one release from each MMA warp) and pre-issue S for the next item after the last stage
-          for (int j = 0; j < NTL; ++j) {
+          for (int j = 0; j < NST; ++j) {
             mbar_wait(BAR(KV_FULL + kslot), kph);
-            if (j + 1 == NTL && next_active) {
+            if (j + 1 == NST && next_active) {
               uint32_t nslot = kslot + 1, nph = kph;
               if (nslot == ATT_STAGES) { nslot = 0; nph ^= 1; }
               wait_q(b ^ 1);
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
     const int OC = HDP / 8;                     // 16-byte chunks per output row and head
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int pair = item % p.NP, sh = item / p.NP;
-      const int nq = min(2, NTL - 2 * pair);
+      const int nq = min(2, p.NQT - 2 * pair);
       if (g >= nq) continue;
       const int qt = 2 * pair + g;
       float m_run = -INFINITY, l_run = 0.f;
@@ -288,8 +291,8 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
         for (int d = 0; d < 32; ++d) o[d] *= alpha;
       }
       fold((int)((uc - 1) & 1));
-      // ---- normalise and store this head's slice of the o image ----
       const int s_idx = sh / p.heads, h = sh - s_idx * p.heads;
+      // ---- normalise and store this head's slice of the o image ----
       const float inv = 1.f / l_run;
       __nv_bfloat16* ob = p.o + (((size_t)s_idx * NTL + qt) * (p.heads * OC) + (size_t)h * OC) * 1024 + (size_t)m * 8;
       for (int c = 0; c < OC; ++c) {
@@ -303,6 +306,119 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// Rows of a sequence that do not fill a 128-row query tile (L mod 128 <= 8: e.g. 1025 = 8*128 + 1, 259 = 2*128 + 3)
+// would each cost a whole tensor-core tile; they run here instead.  One warp per (sequence, head, group of RG tail
+// rows): lanes over keys -- every K and V row is fetched once and used for all RG rows --, shuffle softmax, shuffle
+// reduction of the output.  Same bf16 images, same exp2 domain as the tensor-core kernel.
+template <int RG>
+__global__ void __launch_bounds__(256) attn_tail_rows_kernel(AttnTcParams p, int row0) {
+  const int lane = threadIdx.x & 31;
+  const int n_tail = p.L - row0, n_grp = (n_tail + RG - 1) / RG;
+  const long long total = (long long)p.nseq * p.heads * n_grp;
+  const int HDP = p.HDP, NTL = p.NTL, OC = HDP / 8;
+  const size_t plane = (size_t)p.nseq * p.heads * NTL * HDP * 128;
+  extern __shared__ float tail_sm[];                     // per warp: scores of RG rows x Lpad keys
+  const int Lpad = (p.L + 31) & ~31;
+  float* prob = tail_sm + (size_t)(threadIdx.x >> 5) * RG * Lpad;
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total;
+       w += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int grp = (int)(w % n_grp), sh = (int)(w / n_grp);
+    const int r0 = row0 + grp * RG;
+    const __nv_bfloat16* base = p.qkv + (size_t)sh * NTL * HDP * 128;
+    float qf[RG][32];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      const int row = min(r0 + r, p.L - 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (c < OC) raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(row >> 7) * HDP * 128 + ((size_t)c * 128 + (row & 127)) * 8));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); qf[r][c * 8 + 2 * e] = f.x; qf[r][c * 8 + 2 * e + 1] = f.y; }
+      }
+    }
+    float mx[RG];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) mx[r] = -INFINITY;
+    for (int j = lane; j < Lpad; j += 32) {
+      float sc[RG];
+#pragma unroll
+      for (int r = 0; r < RG; ++r) sc[r] = j < p.L ? 0.f : -INFINITY;
+      if (j < p.L) {
+        const __nv_bfloat16* krow = base + plane + (size_t)(j >> 7) * HDP * 128 + (size_t)(j & 127) * 8;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < OC) {
+            const uint4 kr = __ldg(reinterpret_cast<const uint4*>(krow + (size_t)c * 1024));
+            const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 kf = __bfloat1622float2(k2[e]);
+#pragma unroll
+              for (int r = 0; r < RG; ++r) sc[r] = fmaf(qf[r][c * 8 + 2 * e], kf.x, fmaf(qf[r][c * 8 + 2 * e + 1], kf.y, sc[r]));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RG; ++r) { prob[r * Lpad + j] = sc[r]; mx[r] = fmaxf(mx[r], sc[r]); }
+    }
+#pragma unroll
+    for (int r = 0; r < RG; ++r)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+    // exp2, row sums and P.V in one pass over the keys
+    float sum[RG], acc[RG][32];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      sum[r] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) acc[r][d] = 0.f;
+    }
+    for (int j = lane; j < p.L; j += 32) {
+      float pj[RG];
+#pragma unroll
+      for (int r = 0; r < RG; ++r) { pj[r] = fast_exp2(prob[r * Lpad + j] - mx[r]); sum[r] += pj[r]; }
+      const __nv_bfloat16* vrow = base + 2 * plane + (size_t)(j >> 7) * HDP * 128 + (size_t)(j & 127) * 8;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < OC) {
+          const uint4 vr = __ldg(reinterpret_cast<const uint4*>(vrow + (size_t)c * 1024));
+          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 vf = __bfloat1622float2(v2[e]);
+#pragma unroll
+            for (int r = 0; r < RG; ++r) {
+              acc[r][c * 8 + 2 * e] = fmaf(pj[r], vf.x, acc[r][c * 8 + 2 * e]);
+              acc[r][c * 8 + 2 * e + 1] = fmaf(pj[r], vf.y, acc[r][c * 8 + 2 * e + 1]);
+            }
+          }
+        }
+      }
+    }
+    const int s_idx = sh / p.heads, h = sh - s_idx * p.heads;
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) acc[r][d] += __shfl_xor_sync(0xffffffffu, acc[r][d], o);
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) if (d == lane) mine = acc[r][d];
+      const int row = r0 + r;
+      if (lane < HDP && row < p.L)
+        p.o[(((size_t)s_idx * NTL + (row >> 7)) * (p.heads * OC) + (size_t)h * OC + (lane >> 3)) * 1024 + (size_t)(row & 127) * 8 + (lane & 7)] =
+            __float2bfloat16_rn(mine / sum[r]);
+    }
+    __syncwarp();
+  }
 }
 
 inline uint32_t attn_tc_smem(int HDP) {
