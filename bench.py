@@ -310,8 +310,15 @@ def main():
         k_launches = (lib.tfl_launch_count() - l0) // reps
         k_flops = ffn_call_flops(cfg, B, SEG, 0, 384)
         achieved = k_flops / (k_ms / 1e3) / 1e12
+        traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this very launch shape
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn_ncu_b8.json")))
+            if B == 8 and args.precision == "bf16":
+                traffic = cap["traffic_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak, "traffic": None, "kernel": "conv_swiglu_ffn (freq axis)",
+                            "frac": achieved / peak, "traffic": traffic, "kernel": "conv_swiglu_ffn (freq axis)",
                             "launches_per_call": int(k_launches), "ms_per_call": k_ms, "peak_source": peak_src,
                             "flops_per_call": k_flops}
         del x
