@@ -548,32 +548,50 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = tile / NTL, jt = tile - s * NTL;
       const long long base = p.map.base(s);
-      for (int item = tp; item < 128 * G; item += NPROD) {
-        const int row = item / G, grp = item - row * G;
-        const int j = jt * 128 + row;
-        const bool valid = j < p.L;
-        const float* src = p.x + base + (long long)j * p.map.pos_stride + grp * D;
-        if (D <= 32) {
-          float4 v[8];
+      if (D <= 32) {
+        // two (row, group) items per thread and pass: 16 independent 128-bit loads in flight, x read exactly once
+        for (int item0 = tp; item0 < 128 * G; item0 += 2 * NPROD) {
+          float4 v[2][8];
+          int rowi[2], grpi[2];
+          bool live[2];
 #pragma unroll
-          for (int d = 0; d < 8; ++d)
-            v[d] = (valid && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float ss = 0.f;
+          for (int u = 0; u < 2; ++u) {
+            const int item = item0 + u * NPROD;
+            live[u] = item < 128 * G;
+            rowi[u] = item / G; grpi[u] = item - rowi[u] * G;
+            const int j = jt * 128 + rowi[u];
+            const bool valid = live[u] && j < p.L;
+            const float* src = p.x + base + (long long)j * p.map.pos_stride + grpi[u] * D;
 #pragma unroll
-          for (int d = 0; d < 8; ++d) ss += v[d].x * v[d].x + v[d].y * v[d].y + v[d].z * v[d].z + v[d].w * v[d].w;
-          const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+            for (int d = 0; d < 8; ++d)
+              v[u][d] = (valid && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-          for (int d = 0; d < 8; ++d) {
-            if (4 * d < D) {
-              const int c0 = grp * D + 4 * d;
-              const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
-              uint2 pk;
-              pk.x = pack_bf16(v[d].x * inv * gm.x, v[d].y * inv * gm.y);
-              pk.y = pack_bf16(v[d].z * inv * gm.z, v[d].w * inv * gm.w);
-              *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
+          for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            float ss = 0.f;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) ss += v[u][d].x * v[u][d].x + v[u][d].y * v[u][d].y + v[u][d].z * v[u][d].z + v[u][d].w * v[u][d].w;
+            const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+              if (4 * d < D) {
+                const int c0 = grpi[u] * D + 4 * d;
+                const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+                uint2 pk;
+                pk.x = pack_bf16(v[u][d].x * inv * gm.x, v[u][d].y * inv * gm.y);
+                pk.y = pack_bf16(v[u][d].z * inv * gm.z, v[u][d].w * inv * gm.w);
+                *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + rowi[u]) * 16 + (c0 & 7) * 2) = pk;
+              }
             }
           }
-        } else {
+        }
+      } else {
+        for (int item = tp; item < 128 * G; item += NPROD) {
+          const int row = item / G, grp = item - row * G;
+          const int j = jt * 128 + row;
+          const bool valid = j < p.L;
+          const float* src = p.x + base + (long long)j * p.map.pos_stride + grp * D;
           float ss = 0.f;
           if (valid)
             for (int d = 0; d < D; d += 4) {
@@ -740,7 +758,27 @@ __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
       mbar_wait(BAR(D_FULL + e), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       float* dst = j < p.L ? p.x + p.map.base(s) + (long long)j * p.map.pos_stride : nullptr;
-      for (int c0 = 0; c0 < C; c0 += 16) {
+      int c0 = 0;
+      for (; c0 + 64 <= C; c0 += 64) {     // 64 columns per step: 16 residual loads and 2 TMEM loads in flight together
+        uint32_t r[64];
+        tmem_ld32(lane_addr + e * C + c0, r);
+        tmem_ld32(lane_addr + e * C + c0 + 32, r + 32);
+        float4 xv[16];
+        if (dst != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xv[i] = *reinterpret_cast<const float4*>(dst + c0 + 4 * i);
+        }
+        tc_wait_ld();
+        if (dst != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            xv[i].x += __uint_as_float(r[4 * i]); xv[i].y += __uint_as_float(r[4 * i + 1]);
+            xv[i].z += __uint_as_float(r[4 * i + 2]); xv[i].w += __uint_as_float(r[4 * i + 3]);
+            *reinterpret_cast<float4*>(dst + c0 + 4 * i) = xv[i];
+          }
+        }
+      }
+      for (; c0 < C; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(lane_addr + e * C + c0, r);
         tc_wait_ld();

@@ -52,7 +52,7 @@ inline bool ffn_tc_geometry(int C, int H, int KT, int G, FfnTcGeom* g) {
   g->a_slot_bytes = (uint32_t)(C / 8) * g->AR * 16;
   g->g_buf_bytes = (uint32_t)(TC_HC / 8) * g->AR * 16;
   uint32_t off = 0;
-  g->off_a = off; off += (g->NT + TC_A_EXTRA) * g->a_slot_bytes;
+  g->off_a = off; off += (g->NT == 2 ? g->NT + TC_A_EXTRA : 2) * g->a_slot_bytes;
   g->off_g = off; off += g->NT * g->g_buf_bytes;
   g->off_tab = off; off += (2 * H + 2 * C) * 4;
   off = (off + 15) & ~15u;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = g.C, H = g.H, KT = g.KT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS, NS = g.NS;
   const int KH = g.KH, TPS = g.TPS;
-  constexpr int NA = NT + TC_A_EXTRA;
+  constexpr int NA = NT == 2 ? NT + TC_A_EXTRA : 2;    // A-tile slots (single-tile variant: plain double buffering)
   const uint32_t sbase = smem_u32(smem);
   float* tab_b1 = reinterpret_cast<float*>(smem + g.off_tab);
   float* tab_b2 = tab_b1 + 2 * H;
@@ -629,7 +629,7 @@ inline int tc_ffn(const tfl_plan* pl, const char* packed, int layer, int axis, i
   const FfnPack& f = pl->lay.paths[(size_t)layer * 2 + axis].ffn[j];
   FfnTcGeom g;
   TFL_CHECK(ffn_tc_geometry(c.emb_dim, f.hidden, c.conv_kernel, c.num_groups, &g),
-            "bf16 tcgen05 FFN needs emb_dim %% 16 == 0 (<= 256), ffn_hidden %% 32 == 0, conv1d_kernel <= 8 "
+            "bf16 tcgen05 FFN needs emb_dim %% 16 == 0 (<= 256), ffn_hidden %% 64 == 0, conv1d_kernel <= 8 "
             "(got emb_dim %d, hidden %d, kernel %d); use precision fp32 for this configuration",
             c.emb_dim, f.hidden, c.conv_kernel);
   const int S = axis == TFL_AXIS_FREQ ? F : Tf;

@@ -146,3 +146,33 @@ def test_attention_tc_vs_oracle(pkg, name, cfg, shape):
         sdr = oracle.si_sdr_db(got, branch)
         assert sdr > 35.0, (name, axis, sdr)
         assert float((got - branch).abs().max()) < 0.06 * float(branch.abs().max()) + 1e-3, (name, axis)
+
+
+def test_variant_y_all_layers_bf16(pkg):
+    """configs/musdb18.yaml as committed (hop 512, 4 layers, emb 96, head_dim 24 -> padded to 32): 1.5-s segment, all layers."""
+    cfg = dict(VARIANT_Y, n_layers=4)
+    model = _random_model(pkg, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    mix = _mixture(66150, 1)
+    want = oracle.mss_forward(sd, dict(cfg), mix)
+    model = model.cuda()
+    model.precision = "bf16"
+    with torch.no_grad():
+        got = model(mix.cuda())
+    for k in want:
+        assert oracle.si_sdr_db(got[k].cpu(), want[k]) >= 40.0, k
+
+
+def test_ffn_tc_wide_single_tile_variant(pkg):
+    """emb_dim 256 / hidden 1024 (musdb18_rtx5090_xlarge.yaml widths): the NT = 1 instantiation of the FFN kernel."""
+    cfg = dict(VARIANT_D, emb_dim=256, attention_dim=256, n_heads=16, num_groups=8, ffn_hidden_dim=[1024, 1024])
+    model = _random_model(pkg, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    xin = torch.randn(1, 4, 200, 256, generator=g)
+    model = model.cuda().eval()
+    eng = model._ready()
+    for axis in (0, 1):
+        branch, x0 = _ffn_oracle(sd, cfg, xin, 0, axis, 0)
+        got = eng.ffn_(0, axis, 0, xin.cuda().clone(), 1).cpu() - x0
+        assert oracle.si_sdr_db(got, branch) > 40.0, axis
