@@ -154,6 +154,51 @@ __device__ __forceinline__ void mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_
       : "memory");
 }
 
+// N back-to-back tcgen05.mma whose A / B descriptors advance by a fixed step: one asm block, so the descriptor
+// arithmetic stays in the uniform datapath instead of a register -> uniform-register transfer per MMA.
+template <int N>
+__device__ __forceinline__ void mma_burst(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                          uint32_t acc_first, uint32_t a_step, uint32_t b_step) {
+  static_assert(N == 1 || N == 2 || N == 4, "burst length");
+  if constexpr (N == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 a1, %1, %6;\n\tadd.u32 a2, a1, %6;\n\tadd.u32 a3, a2, %6;\n\t"
+        "add.u32 b1, %2, %7;\n\tadd.u32 b2, b1, %7;\n\tadd.u32 b3, b2, %7;\n\t"
+        "mov.b64 ad, {%1, %3};\n\tmov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n\t"
+        "mov.b64 ad, {a1, %3};\n\tmov.b64 bd, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, 1;\n\t"
+        "mov.b64 ad, {a2, %3};\n\tmov.b64 bd, {b2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, 1;\n\t"
+        "mov.b64 ad, {a3, %3};\n\tmov.b64 bd, {b3, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, 1;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(b_step)
+        : "memory");
+  } else if constexpr (N == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a1, b1;\n\t.reg .b64 ad, bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 a1, %1, %6;\n\tadd.u32 b1, %2, %7;\n\t"
+        "mov.b64 ad, {%1, %3};\n\tmov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n\t"
+        "mov.b64 ad, {a1, %3};\n\tmov.b64 bd, {b1, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, 1;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(b_step)
+        : "memory");
+  } else {
+    mma_lohi(d_tmem, a_lo, hi, b_lo, hi, idesc, acc_first);
+  }
+}
+// n MMAs (any n) as bursts of 4 / 2 / 1
+__device__ __forceinline__ void mma_run(int n, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                        uint32_t acc_first, uint32_t a_step, uint32_t b_step) {
+  while (n >= 4) { mma_burst<4>(d_tmem, a_lo, b_lo, hi, idesc, acc_first, a_step, b_step); a_lo += 4 * a_step; b_lo += 4 * b_step; acc_first = 1; n -= 4; }
+  if (n >= 2) { mma_burst<2>(d_tmem, a_lo, b_lo, hi, idesc, acc_first, a_step, b_step); a_lo += 2 * a_step; b_lo += 2 * b_step; acc_first = 1; n -= 2; }
+  if (n >= 1) mma_burst<1>(d_tmem, a_lo, b_lo, hi, idesc, acc_first, a_step, b_step);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom g) {
   using namespace tc;
@@ -255,12 +300,9 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
               for (int tl = 0; tl < TPS; ++tl) {
                 const int tap = s * TPS + tl;
                 if (tap >= KT) break;
-                if (elect_one()) {
-#pragma unroll
-                  for (uint32_t kk = 0; kk < TC_HC / 16; ++kk)
-                    mma_lohi(dcol, (gb + tap + kk * 2 * AR) | lo_a, hi, (wb + tl * tap16 + kk * 2 * C) | lo_b2, hi, idesc2,
-                             (uint32_t)(cc | tap | (int)kk));
-                }
+                if (elect_one())
+                  mma_run(TC_HC / 16, dcol, (gb + tap) | lo_a, (wb + tl * tap16) | lo_b2, hi, idesc2, (uint32_t)(cc | tap),
+                          2u * AR, 2u * C);
                 __syncwarp();
               }
             }
@@ -290,11 +332,8 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
               _Pragma("unroll") for (int t = 0; t < NT; ++t) {
                 const uint32_t ab = a16 + aslot[t] * aslot16 + k + hf * KK1 * 2 * AR;
                 const uint32_t dcol = tmem + t * (2 * TC_HC);
-                if (elect_one()) {
-                  for (uint32_t kk = 0; kk < KK1; ++kk)
-                    mma_lohi(dcol, (ab + kk * 2 * AR) | lo_a, hi, (wb + kk * 2 * 128) | lo_b1, hi, idesc1,
-                             (uint32_t)(k | hf | (int)kk));
-                }
+                if (elect_one())
+                  mma_run((int)KK1, dcol, ab | lo_a, wb | lo_b1, hi, idesc1, (uint32_t)(k | hf), 2u * AR, 256u);
                 __syncwarp();
               }
               if (elect_one()) mma_commit(BAR(W_EMPTY + wslot));
