@@ -131,6 +131,11 @@ int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan,
                        int n_bands, int n_src, const int64_t* table, const float* weights, float* est, int masking,
                        tfl_stream_t stream);
 
+/* Diagnostic: process-wide switches used for A/B measurements (not part of the reference-facing surface).
+ *   TFL_OPT_ATTN_KERNEL  1 = attn_tc_kernel (P through shared memory), 2 = attn_tc2_kernel (P in TMEM; default) */
+enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_COUNT = 4 };
+int tfl_debug_set_option(int key, int value);
+
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN
  * kernel records clock64() stamps of its pipeline events ([event * 64 + chunk index]). */
 int tfl_debug_set_trace(void* device_buffer);
@@ -138,6 +143,7 @@ int tfl_debug_set_trace(void* device_buffer);
 /* Diagnostic: exercises the tcgen05 plumbing of the bf16 path on one 128-row tile.
  * mode 0: D[128, N] = sum_{tap < taps} A[m + tap, :] . B[tap][n, :]   A [128 + taps - 1, Kd], B [taps, N, Kd]
  * mode 1: D[128, N] = A[m, :] . B[:, n]                               A [128, Kd], B [Kd, N] (N-contiguous)
+ * mode 2: as mode 1 with A staged in TMEM (tcgen05.st) instead of shared memory; N <= 128, Kd <= 256
  * Operands are rounded to bf16, accumulation is fp32.  scratch: >= taps * N * Kd * 2 bytes. */
 int tfl_tc_selftest(const float* A, const float* B, float* D, void* scratch, int N, int Kd, int taps, int mode,
                     tfl_stream_t stream);

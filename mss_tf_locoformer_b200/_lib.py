@@ -42,6 +42,7 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_segment_ola": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "tfl_bs_band_split": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tfl_bs_band_decode": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "tfl_debug_set_option": (_I, [_I, _I]),
     "tfl_debug_set_trace": (_I, [_P]),
     "tfl_debug_timeout": (_I, [C.POINTER(C.c_uint32), _I]),
     "tfl_tc_selftest": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

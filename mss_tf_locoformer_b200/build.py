@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtfl_b200.so")
 SOURCES = ["tfl_api.cu"]
-HEADERS = ["common.cuh", "kernels_f32.cuh", "kernels_tc.cuh", "kernels_attn.cuh", "kernels_bs.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "tfl.h")]
+HEADERS = ["common.cuh", "kernels_f32.cuh", "kernels_tc.cuh", "kernels_attn.cuh", "kernels_attn2.cuh", "kernels_bs.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "tfl.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,0 +1,401 @@
+// K5 (v2)  attn_tc2_kernel: softmax(q k^T) v per (sequence, head) on tcgen05 / TMEM
+// (models/mss_tflocoformer.py:523-531), same bf16 tile images in / out as kernels_attn.cuh.
+//
+// With head_dim 32 there are only 128 MMA FLOPs per exponential, so the kernel is paced by the 16/clk/SM exp2 unit
+// and by whatever else the softmax threads must issue per score.  v2 strips that to the minimum:
+//   * P never touches shared memory: the softmax threads write bf16 probabilities straight into TMEM
+//     (tcgen05.st) and P.V runs with its A operand in TMEM -- no st.shared, no proxy fence, and the shared-memory
+//     pipe only serves Q / K / V operand reads;
+//   * O accumulates in TMEM over the whole key range (accumulating MMAs); nothing is folded per unit.  The softmax
+//     reference m_ref is the row maximum of the first 32 keys and is only raised -- with a rescale of the TMEM
+//     accumulator by the softmax thread itself -- when a later score exceeds it by more than 2^ATT2_TH
+//     (bf16 / fp32 share an 8-bit exponent: a stale reference costs range, not precision);
+//   * scores are consumed in halves of 32 keys (one tcgen05.ld, one max3 tree, 32 exp2, one tcgen05.st), each half
+//     published separately, so a thread holds 32 + 16 registers of tile data and FOUR softmax groups (16 warps,
+//     4 per SM sub-partition) fit next to the MMA warps -- enough warps in flight to keep the exp2 unit busy while
+//     others wait on TMEM loads or barriers;
+//   * the key range ends in a unit of N = ceil16(remaining keys) columns instead of a masked 64-key unit
+//     (1025 = 16*64 + 1, 259 = 4*64 + 3).
+//
+// One persistent CTA per SM; work item = (sequence, group of HG heads, group of QG query tiles), QG * HG = 4:
+// the frequency axis (8 query tiles) runs 4 tiles of one head per item, the time axis (2 tiles) 2 tiles x 2 heads.
+//   warps 0-15    four softmax groups, one query row per thread
+//   warps 16-19   one MMA warp per group: S = Q K^T (64 keys ahead of the softmax), O += P_half V
+//   warp 20       loader: Q tiles (double-buffered per item), K/V ring (one stage = 128 keys of K and V per head)
+// TMEM per group g (128 columns): S [0,64)  P half 0 [64,80)  P half 1 [80,96)  O [96,96+HDP)
+#pragma once
+#include "kernels_attn.cuh"
+
+namespace tfl {
+
+struct Attn2Params {
+  const __nv_bfloat16* qkv; __nv_bfloat16* o;
+  int nseq, heads, L, NTL, HDP;
+  int NQT;       // full query tiles handled here (trailing rows may go to attn_tail_rows_kernel)
+  int NU;        // 64-key units per sequence (the last one may be short)
+  int QG, HG;    // query tiles / heads per work item
+  int NQG, NHG;  // query-tile groups / head groups per sequence
+  int NS;        // K/V ring stages
+  int n_items;
+};
+
+constexpr int ATT2_G = 4;
+constexpr int ATT2_THREADS = 32 * (4 * ATT2_G + ATT2_G + 1);   // softmax warps, MMA warps, loader
+constexpr float ATT2_TH = 16.f;    // raise the softmax reference when a score exceeds it by more than this (log2 units)
+
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem] from 32-bit descriptor halves
+__device__ __forceinline__ void mma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+inline uint32_t attn2_smem(int HDP, int HG, int* NS_out) {
+  const uint32_t tile = (uint32_t)HDP * 128 * 2;
+  const uint32_t fixed = 2u * ATT2_G * tile + 512;
+  const uint32_t stage = (uint32_t)HG * 2 * tile;
+  int NS = (int)((TC_SMEM_MAX - fixed) / stage);
+  if (NS > 8) NS = 8;
+  *NS_out = NS;
+  return fixed + (uint32_t)NS * stage;
+}
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p) {
+  using namespace tc;
+  constexpr int G = ATT2_G;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HDP = p.HDP, NTL = p.NTL, NU = p.NU, QG = p.QG, HG = p.HG, NS = p.NS;
+  const int NST = (NU + 1) / 2;                                  // K/V ring stages (128 keys) per item
+  const uint32_t tile_bytes = (uint32_t)HDP * 128 * 2;          // one Q / K / V tile (128 rows)
+  const uint32_t stage_bytes = (uint32_t)HG * 2 * tile_bytes;   // per head: K tile, V tile
+  const uint32_t off_q = 0, off_kv = 2u * G * tile_bytes, off_bar = off_kv + (uint32_t)NS * stage_bytes;
+  const uint32_t sbase = smem_u32(smem);
+  auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
+  const int KV_FULL = 0, KV_EMPTY = 8, Q_FULL = 16, Q_EMPTY = 18, S_FULL = 20, S_EMPTY = 24, P_FULL = 28, PV_DONE = 36;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 48);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), G); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), G); }
+    for (int g = 0; g < G; ++g) {
+      mbar_init(BAR(S_FULL + g), 1); mbar_init(BAR(S_EMPTY + g), 128);
+      for (int h = 0; h < 2; ++h) { mbar_init(BAR(P_FULL + g * 2 + h), 128); mbar_init(BAR(PV_DONE + g * 2 + h), 1); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 * G) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const size_t which_stride = (size_t)p.nseq * p.heads * NTL * HDP * 128;   // elements between the q, k, v planes
+  const int n_last = p.L - (NU - 1) * 64;                                   // keys in the last unit (1..64)
+
+  // item -> (sequence, first head, first query tile); group g -> (head, tile)
+  auto decode = [&](int item, int& seq, int& h0, int& q0) {
+    const int qg = item % p.NQG, t = item / p.NQG;
+    q0 = qg * QG; h0 = (t % p.NHG) * HG; seq = t / p.NHG;
+  };
+  auto group_active = [&](int g, int h0, int q0) { return h0 + g / QG < p.heads && q0 + g % QG < p.NQT; };
+
+  if (warp == 5 * G) {
+    // ===================== loader =====================
+    uint32_t kslot = 0, kph = 0, qph = 0;
+    int n_local = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
+      int seq, h0, q0;
+      decode(item, seq, h0, q0);
+      const int b = n_local & 1;
+      mbar_wait(BAR(Q_EMPTY + b), ((qph >> b) & 1) ^ 1);
+      qph ^= 1u << b;
+      if (elect_one()) {
+        int n_act = 0;
+        for (int g = 0; g < G; ++g) n_act += group_active(g, h0, q0) ? 1 : 0;
+        mbar_arrive_expect_tx(BAR(Q_FULL + b), n_act * tile_bytes);
+        for (int g = 0; g < G; ++g) {
+          if (!group_active(g, h0, q0)) continue;
+          const size_t sh = (size_t)seq * p.heads + h0 + g / QG;
+          bulk_g2s(sbase + off_q + (b * G + g) * tile_bytes, p.qkv + (sh * NTL + q0 + g % QG) * HDP * 128, tile_bytes,
+                   BAR(Q_FULL + b));
+        }
+      }
+      __syncwarp();
+      const int nh = min(HG, p.heads - h0);
+      for (int j = 0; j < NST; ++j) {
+        mbar_wait(BAR(KV_EMPTY + kslot), kph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(BAR(KV_FULL + kslot), nh * 2 * tile_bytes);
+          for (int hh = 0; hh < nh; ++hh) {
+            const __nv_bfloat16* src = p.qkv + (((size_t)seq * p.heads + h0 + hh) * NTL + j) * HDP * 128;
+            const uint32_t dst = sbase + off_kv + kslot * stage_bytes + hh * 2 * tile_bytes;
+            bulk_g2s(dst, src + which_stride, tile_bytes, BAR(KV_FULL + kslot));
+            bulk_g2s(dst + tile_bytes, src + 2 * which_stride, tile_bytes, BAR(KV_FULL + kslot));
+          }
+        }
+        __syncwarp();
+        if (++kslot == (uint32_t)NS) { kslot = 0; kph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 * G) {
+    // ===================== MMA warp of group g =====================
+    // S for unit u+1 (or unit 0 of the next item) is issued between the two P.V halves of unit u, so a softmax
+    // group finds its next scores in TMEM when it gets there.  The whole warp runs the control flow; one elected
+    // lane issues.
+    const int g = warp - 4 * G;
+    const int hh = g / QG;                                         // head slot of this group inside a K/V stage
+    const uint32_t tcol = tmem + g * 128;
+    const uint32_t idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
+    const uint32_t idesc_s_full = instr_desc(128, 64), idesc_s_last = instr_desc(128, (n_last + 15) & ~15);
+    const uint32_t hi_k = (128u >> 4) | (1u << 14);              // K-major tiles: SBO = 128 B
+    const uint32_t lo_k = 128u << 16;                            //   128-row tiles: LBO = 128 rows * 16 B
+    const uint32_t hi_v = ((128u * 16) >> 4) | (1u << 14);       // V as MN-major: SBO = 2048 B (next 8 columns)
+    const uint32_t lo_v = (128u >> 4) << 16;                     //                LBO = 128 B (next 8 kv rows)
+    const uint32_t q16 = (sbase + off_q) >> 4, kv16 = (sbase + off_kv) >> 4;
+    const uint32_t tile16 = tile_bytes >> 4, stage16 = stage_bytes >> 4;
+    uint32_t kslot = 0, kph = 0, qph = 0;
+    uint32_t us = 0, up = 0;                                       // running unit counters: S issued, P.V consumed
+    auto issue_s = [&](int b, uint32_t slot, int half, bool last_unit, bool last_of_item) {
+      mbar_wait(BAR(S_EMPTY + g), (us & 1) ^ 1);
+      ++us;
+      tc_fence_after();
+      const uint32_t qa = q16 + (b * G + g) * tile16, kb = kv16 + slot * stage16 + hh * 2 * tile16 + half * 64;
+      const uint32_t idesc = last_unit ? idesc_s_last : idesc_s_full;
+      if (elect_one()) {
+        for (int kk = 0; kk < HDP / 16; ++kk)
+          mma_lohi(tcol, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc, (uint32_t)kk);
+        mma_commit(BAR(S_FULL + g));
+        if (last_of_item) mma_commit(BAR(Q_EMPTY + b));
+      }
+      __syncwarp();
+    };
+    auto wait_q = [&](int b) {
+      mbar_wait(BAR(Q_FULL + b), (qph >> b) & 1);
+      qph ^= 1u << b;
+    };
+    auto next_slot = [&](uint32_t& nslot, uint32_t& nph) {
+      nslot = kslot + 1; nph = kph;
+      if (nslot == (uint32_t)NS) { nslot = 0; nph ^= 1; }
+    };
+    auto release_kv = [&](bool by_commit) {
+      if (elect_one()) {
+        if (by_commit) mma_commit(BAR(KV_EMPTY + kslot)); else mbar_arrive(BAR(KV_EMPTY + kslot));
+      }
+      __syncwarp();
+      if (++kslot == (uint32_t)NS) { kslot = 0; kph ^= 1; }
+    };
+    auto item_active = [&](int item) {
+      if (item >= p.n_items) return false;
+      int seq, h0, q0;
+      decode(item, seq, h0, q0);
+      return group_active(g, h0, q0);
+    };
+    int n_local = 0;
+    if (item_active(blockIdx.x)) {                                 // S of the very first unit
+      wait_q(0);
+      mbar_wait(BAR(KV_FULL + kslot), kph);
+      tc_fence_after();
+      issue_s(0, kslot, 0, NU == 1, NU == 1);
+    }
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
+      const bool active = item_active(item);
+      const int b = n_local & 1;
+      const bool next_active = item_active(item + gridDim.x);
+      if (!active) {
+        // no work for this group in the item: keep the ring / Q protocols alive (their barriers expect one arrival
+        // per MMA warp) and pre-issue S for the next item after the last stage
+        wait_q(b);
+        if (elect_one()) mbar_arrive(BAR(Q_EMPTY + b));
+        __syncwarp();
+        for (int j = 0; j < NST; ++j) {
+          mbar_wait(BAR(KV_FULL + kslot), kph);
+          if (j + 1 == NST && next_active) {
+            uint32_t nslot, nph;
+            next_slot(nslot, nph);
+            wait_q(b ^ 1);
+            mbar_wait(BAR(KV_FULL + nslot), nph);
+            tc_fence_after();
+            issue_s(b ^ 1, nslot, 0, NU == 1, NU == 1);
+          }
+          release_kv(false);
+        }
+        continue;
+      }
+      for (int u = 0; u < NU; ++u) {
+        const int half = u & 1;
+        uint32_t nslot, nph;
+        next_slot(nslot, nph);
+        const int nk = min(64, p.L - u * 64);
+        const int nch = (nk + 15) >> 4, nch0 = min(nch, 2), nch1 = nch - nch0;    // 16-key MMA steps per half
+        const uint32_t vb = kv16 + kslot * stage16 + hh * 2 * tile16 + tile16 + half * 64;
+        // ---- O (+)= P[half 0] . V ----
+        mbar_wait(BAR(P_FULL + g * 2), up & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int c = 0; c < nch0; ++c)
+            mma_ts_lohi(tcol + 96, tcol + 64 + c * 8, (vb + c * 16) | lo_v, hi_v, idesc_pv, (uint32_t)(u | c));
+          mma_commit(BAR(PV_DONE + g * 2));
+        }
+        __syncwarp();
+        // ---- S for the next unit ----
+        if (u + 1 < NU) {
+          if (half == 1) { mbar_wait(BAR(KV_FULL + nslot), nph); tc_fence_after(); }
+          issue_s(b, half == 1 ? nslot : kslot, half ^ 1, u + 2 == NU, u + 2 == NU);
+        } else if (next_active) {
+          wait_q(b ^ 1);
+          mbar_wait(BAR(KV_FULL + nslot), nph);
+          tc_fence_after();
+          issue_s(b ^ 1, nslot, 0, NU == 1, NU == 1);
+        }
+        // ---- O += P[half 1] . V ----
+        mbar_wait(BAR(P_FULL + g * 2 + 1), up & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int c = 0; c < nch1; ++c)
+            mma_ts_lohi(tcol + 96, tcol + 80 + c * 8, (vb + (2 + c) * 16) | lo_v, hi_v, idesc_pv, 1u);
+          mma_commit(BAR(PV_DONE + g * 2 + 1));
+        }
+        __syncwarp();
+        ++up;
+        if (half == 1 || u + 1 == NU) release_kv(true);            // this group is done with the K/V stage
+      }
+    }
+  } else {
+    // ===================== softmax groups =====================
+    const int g = warp >> 2;
+    const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;
+    const uint32_t tcol = tmem + ((uint32_t)(quarter * 32) << 16) + g * 128;
+    const int OC = HDP / 8;
+    uint32_t uc = 0;                                               // running unit counter of this group
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int seq, h0, q0;
+      decode(item, seq, h0, q0);
+      if (!group_active(g, h0, q0)) continue;
+      const int head = h0 + g / QG, qt = q0 + g % QG;
+      float m_ref = 0.f, l0 = 0.f, l1 = 0.f;
+      for (int u = 0; u < NU; ++u, ++uc) {
+        const int nk = min(64, p.L - u * 64);
+        mbar_wait(BAR(S_FULL + g), uc & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int nkh = min(32, nk - 32 * h);                    // valid keys in this half (<= 0: empty)
+          // P[h] is free once P.V of the previous unit's half h has completed.  Waited for in EVERY half, also the
+          // empty ones: a parity wait is only meaningful for the phase right after the last one this thread has seen.
+          if (uc > 0) { mbar_wait(BAR(PV_DONE + g * 2 + h), (uc - 1) & 1); tc_fence_after(); }
+          if (nkh > 0) {
+            uint32_t s[32];
+            tmem_ld32(tcol + h * 32, s);
+            tc_wait_ld();
+            if (h == 1 || nk <= 32) { tc_fence_before(); mbar_arrive(BAR(S_EMPTY + g)); }   // scores are in registers
+            if (nkh < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i >= nkh) s[i] = 0xff800000u;   // -inf: columns beyond the sequence
+            }
+            float mx[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float t = max3f(__uint_as_float(s[8 * c]), __uint_as_float(s[8 * c + 1]), __uint_as_float(s[8 * c + 2]));
+              t = max3f(t, __uint_as_float(s[8 * c + 3]), __uint_as_float(s[8 * c + 4]));
+              mx[c] = max3f(t, __uint_as_float(s[8 * c + 5]), __uint_as_float(s[8 * c + 6]));
+            }
+            const float mxh = max3f(max3f(mx[0], mx[1], mx[2]), max3f(mx[3], __uint_as_float(s[7]), __uint_as_float(s[15])),
+                                    fmaxf(__uint_as_float(s[23]), __uint_as_float(s[31])));
+            if (u == 0 && h == 0) {
+              m_ref = mxh;
+            } else if (__any_sync(0xffffffffu, mxh > m_ref + ATT2_TH)) {
+              // rare: raise the reference and rescale what has been accumulated so far.  Every P.V issued so far must
+              // have landed: the latest one consumed the other half (of this unit for h = 1, of the previous for h = 0).
+              const float m_new = mxh > m_ref + ATT2_TH ? mxh : m_ref;
+              const float alpha = fast_exp2(m_ref - m_new);
+              mbar_wait(BAR(PV_DONE + g * 2 + (h ^ 1)), (h == 1 ? uc : uc - 1) & 1);
+              tc_fence_after();
+              for (int c0 = 0; c0 < HDP; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tcol + 96 + c0, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                tmem_st16(tcol + 96 + c0, r);
+              }
+              tc_wait_st();
+              l0 *= alpha; l1 *= alpha;
+              m_ref = m_new;
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float p0 = fast_exp2(__uint_as_float(s[2 * i]) - m_ref);
+              const float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - m_ref);
+              l0 += p0; l1 += p1;
+              pk[i] = pack_bf16(p0, p1);
+            }
+            if (nkh > 16) {
+#pragma unroll
+              for (int i = 8; i < 16; ++i) {
+                const float p0 = fast_exp2(__uint_as_float(s[2 * i]) - m_ref);
+                const float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - m_ref);
+                l0 += p0; l1 += p1;
+                pk[i] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 8; i < 16; ++i) pk[i] = 0u;
+            }
+            tmem_st16(tcol + 64 + h * 16, pk);
+            tc_wait_st();
+          }
+          tc_fence_before();
+          mbar_arrive(BAR(P_FULL + g * 2 + h));
+        }
+      }
+      // ---- all keys done: O / l -> this head's slice of the o image ----
+      mbar_wait(BAR(PV_DONE + g * 2 + 1), (uc - 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld16(tcol + 96, r);
+      if (HDP > 16) tmem_ld16(tcol + 96 + 16, r + 16);
+      tc_wait_ld();
+      const float inv = 1.f / (l0 + l1);
+      __nv_bfloat16* ob = p.o + (((size_t)seq * NTL + qt) * (p.heads * OC) + (size_t)head * OC) * 1024 + (size_t)m * 8;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < OC) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = pack_bf16(__uint_as_float(r[c * 8 + 2 * e]) * inv, __uint_as_float(r[c * 8 + 2 * e + 1]) * inv);
+          *reinterpret_cast<uint4*>(ob + (size_t)c * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4 * G) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tfl

@@ -559,6 +559,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
 // Self-test of the tcgen05 plumbing (descriptors, row-shifted taps, bulk copy, TMEM round trip):
 // D[128, N] = sum_tap A[m + tap, :] . B_tap[n, :]   (mode 0: B K-major, staged by a bulk copy)
 // D[128, N] = A[m, :] . V[:, n]                     (mode 1: V MN-major, rows of V are the K index)
+// same with A staged in TMEM by tcgen05.st          (mode 2: the P.V form of attn_tc2_kernel; N <= 128)
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                              const __nv_bfloat16* __restrict__ Bimg,
@@ -576,12 +577,12 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < AR * Kd; i += blockDim.x) {
     const int r = i / Kd, c = i % Kd;
     *reinterpret_cast<__nv_bfloat16*>(sa + ((size_t)(c >> 3) * AR + r) * 16 + (c & 7) * 2) = __float2bfloat16_rn(A[i]);
   }
-  if (mode == 1) {
+  if (mode >= 1) {
     for (int i = threadIdx.x; i < Kd * N; i += blockDim.x) {
       const int r = i / N, c = i % N;  // V[r = k index][c = n index]
       *reinterpret_cast<__nv_bfloat16*>(sb + ((size_t)(c >> 3) * Kd + r) * 16 + (c & 7) * 2) = __float2bfloat16_rn(B[i]);
@@ -592,6 +593,20 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (mode == 2) {
+    // row m of A as packed bf16 pairs in TMEM columns [256, 256 + Kd/2): thread m owns lane m
+    const int m = warp * 32 + lane;
+    for (int c0 = 0; c0 < Kd; c0 += 32) {
+      uint32_t r[16];
+      for (int e = 0; e < 16; ++e)
+        r[e] = c0 + 2 * e < Kd ? pack_bf16(A[(size_t)m * Kd + c0 + 2 * e], A[(size_t)m * Kd + c0 + 2 * e + 1]) : 0u;
+      tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0 / 2, r);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (threadIdx.x == 0) {
     if (mode == 0) {
       mbar_arrive_expect_tx(smem_u32(&bars[0]), taps * b_tap_bytes);
@@ -611,7 +626,8 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
         const uint64_t ad = smem_desc(smem_u32(sa) + kk * 2 * AR * 16, AR * 16, 128);
         // MN-major: LBO = 128 B between 8-row K groups, SBO = Kd*16 between 8-column N groups
         const uint64_t bd = smem_desc(smem_u32(sb) + kk * 16 * 16, 128, Kd * 16);
-        mma_ss(tmem, ad, bd, idesc, kk != 0);
+        if (mode == 1) mma_ss(tmem, ad, bd, idesc, kk != 0);
+        else mma_ts(tmem, tmem + 256 + kk * 8, bd, idesc, kk != 0);
       }
     }
     mma_commit(smem_u32(&bars[1]));
@@ -627,7 +643,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 __global__ void tc_selftest_pack_kernel(const float* __restrict__ B, __nv_bfloat16* __restrict__ img, int N, int Kd, int taps) {
@@ -642,7 +658,8 @@ __global__ void tc_selftest_pack_kernel(const float* __restrict__ B, __nv_bfloat
 inline int tc_selftest(const float* A, const float* B, float* D, void* scratch, int N, int Kd, int taps, int mode,
                        cudaStream_t st) {
   TFL_CHECK(N % 16 == 0 && N <= 256 && Kd % 16 == 0 && taps >= 1 && taps <= 8, "selftest shape");
-  TFL_CHECK(mode == 0 || taps == 1, "mode 1 uses a single tap");
+  TFL_CHECK(mode == 0 || taps == 1, "modes 1 and 2 use a single tap");
+  TFL_CHECK(mode != 2 || (N <= 128 && Kd <= 256), "mode 2 shape");
   const int AR = 128 + taps - 1;
   const size_t a_bytes = ((size_t)(Kd / 8) * AR * 16 + 127) & ~(size_t)127;
   const size_t b_bytes = ((size_t)taps * N * Kd * 2 + 127) & ~(size_t)127;

@@ -10,11 +10,13 @@
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_attn.cuh"
+#include "kernels_attn2.cuh"
 #include "kernels_bs.cuh"
 
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
+static int g_options[TFL_OPT_COUNT] = {2, 0, 0, 0};   // tfl_debug_set_option
 unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -347,7 +349,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
   __nv_bfloat16* oimg = (__nv_bfloat16*)(wsp + ws.o_img);
   float2* rope = (float2*)(wsp + ws.rope);
   const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
-  static thread_local uint32_t smem_set[3] = {0, 0, 0};
+  static thread_local uint32_t smem_set[4] = {0, 0, 0, 0};
   if (c.rope) {
     rope_table_kernel<<<(L * (HDP / 2) + 255) / 256, 256, 0, st>>>(rope, (const float*)(packed + p.rope), L, hd / 2, HDP / 2);
     TFL_LAUNCH_CHECK();
@@ -368,23 +370,39 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     TFL_LAUNCH_CHECK();
   }
   {
-    AttnTcParams ap;
-    ap.qkv = qkv; ap.o = oimg; ap.nseq = nseq; ap.heads = heads; ap.L = L; ap.NTL = NTL; ap.HDP = HDP;
     // query rows that do not fill a tile run on CUDA cores when there are only a few of them (1025 = 8*128 + 1,
     // 259 = 2*128 + 3): a mostly empty tensor-core tile costs as much as a full one
-    // (measured: -2.4 ms per 4-segment forward; doing the same for trailing KEYS inside the kernel cost more than
-    // the masked partial unit it saved, so keys keep the masked unit)
     const int tail_q = (L > 128 && L % 128 != 0 && L % 128 <= 8) ? L % 128 : 0;
+    AttnTcParams ap;
+    ap.qkv = qkv; ap.o = oimg; ap.nseq = nseq; ap.heads = heads; ap.L = L; ap.NTL = NTL; ap.HDP = HDP;
     ap.NQT = tail_q ? L / 128 : NTL;
     ap.NU = (L + 63) / 64;
     ap.NP = (ap.NQT + 1) / 2; ap.n_items = nseq * heads * ap.NP;
-    const uint32_t smem = attn_tc_smem(HDP);
-    if (smem > smem_set[1]) {
-      TFL_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[1] = smem;
+    if (g_options[TFL_OPT_ATTN_KERNEL] == 1) {
+      const uint32_t smem = attn_tc_smem(HDP);
+      if (smem > smem_set[1]) {
+        TFL_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[1] = smem;
+      }
+      const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
+      attn_tc_kernel<<<grid, 352, smem, st>>>(ap);
+    } else {
+      Attn2Params a2;
+      a2.qkv = qkv; a2.o = oimg; a2.nseq = nseq; a2.heads = heads; a2.L = L; a2.NTL = NTL; a2.HDP = HDP;
+      a2.NQT = ap.NQT; a2.NU = ap.NU;
+      a2.QG = a2.NQT >= 3 ? 4 : (a2.NQT == 2 ? 2 : 1);         // 4 groups = QG query tiles x HG heads
+      a2.HG = ATT2_G / a2.QG;
+      a2.NQG = (a2.NQT + a2.QG - 1) / a2.QG; a2.NHG = (heads + a2.HG - 1) / a2.HG;
+      a2.n_items = nseq * a2.NHG * a2.NQG;
+      const uint32_t smem = attn2_smem(HDP, a2.HG, &a2.NS);
+      TFL_CHECK(a2.NS >= 2, "attention K/V ring does not fit in shared memory");
+      if (smem > smem_set[3]) {
+        TFL_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[3] = smem;
+      }
+      const int grid = a2.n_items < pl->sm_count ? a2.n_items : pl->sm_count;
+      attn_tc2_kernel<<<grid, ATT2_THREADS, smem, st>>>(a2);
     }
-    const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
-    attn_tc_kernel<<<grid, 352, smem, st>>>(ap);
     TFL_LAUNCH_CHECK();
     if (tail_q) {
       const int Lpad = (L + 31) & ~31;
@@ -672,6 +690,12 @@ int tfl_bs_band_decode(const float* x, const float* spec, int B, int M, int T, i
   bs_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, spec, M, T, F, C, nb, n_src, (const long long*)table, weights,
                                                               est, masking, 1e-5f);
   TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+int tfl_debug_set_option(int key, int value) {
+  TFL_CHECK(key >= 0 && key < TFL_OPT_COUNT, "unknown option %d", key);
+  g_options[key] = value;
   return 0;
 }
 

@@ -45,6 +45,18 @@ def test_tc_selftest_mn_major_b(pkg, N, Kd):
     assert float((D - want).abs().max()) < 2e-3 * Kd ** 0.5
 
 
+@pytest.mark.parametrize("N,Kd", [(32, 64), (32, 32), (16, 16), (64, 128)])
+def test_tc_selftest_a_in_tmem(pkg, N, Kd):
+    """P.V form of attn_tc2_kernel: A staged in TMEM by tcgen05.st as packed bf16 pairs, V MN-major in smem."""
+    from mss_tf_locoformer_b200.engine import tc_selftest
+    g = torch.Generator().manual_seed(7 * N + Kd)
+    A = torch.randn(128, Kd, generator=g)
+    V = torch.randn(Kd, N, generator=g)
+    D = tc_selftest(A.cuda(), V.cuda(), 1, 2).cpu()
+    want = (_bf16(A).double() @ _bf16(V).double()).float()
+    assert float((D - want).abs().max()) < 2e-3 * Kd ** 0.5
+
+
 def _ffn_oracle(sd, cfg, xin, layer, axis, j):
     path = "freq_path" if axis == 0 else "frame_path"
     p = f"blocks.{layer}.{path}"
