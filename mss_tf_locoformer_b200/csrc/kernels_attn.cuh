@@ -673,12 +673,19 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
 // proj_tc_kernel: x += o . Wo^T (head merge + residual, :536-540, :456).  A tiles are the attention kernel's o
 // images (one bulk copy each), Wo stays resident in smem, accumulators double-buffered in TMEM.
 //   warp 0: loader   warp 1: MMA thread   warps 2-9: two epilogue groups alternating tiles
+// Epilogue (C % 64 == 0): TMEM hands every thread one ROW of the tile, but a warp instruction that touches 32 rows
+// of x costs 32 L1 tag cycles -- 8 k cycles per tile, which was the kernel's whole run time.  So the update goes
+// through a padded staging tile in shared memory, 64 columns at a time: row-per-thread in, then each warp walks
+// its 32 rows with half a warp per row (256 contiguous bytes): the read-modify-write of x is 4 lines per
+// instruction instead of 32.
 // --------------------------------------------------------------------------------------------
 struct ProjTcParams {
   const __nv_bfloat16* oimg; const char* wimg; float* x; SeqMap map;
   int C, AP, L, NTL, n_tiles;
 };
-constexpr int PROJ_STAGES = 4;
+constexpr int PROJ_STAGES = 3;
+constexpr uint32_t PROJ_STG_PITCH = 64 * 4 + 16;                // staging row: 64 fp32 + 16 B (conflict-free both ways)
+constexpr uint32_t PROJ_STG_BYTES = 128 * PROJ_STG_PITCH;
 
 __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
   using namespace tc;
@@ -686,7 +693,7 @@ __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C, AP = p.AP, NTL = p.NTL;
   const uint32_t w_bytes = (uint32_t)AP * C * 2, a_bytes = (uint32_t)AP * 128 * 2;
-  const uint32_t off_w = 0, off_a = w_bytes, off_bar = off_a + PROJ_STAGES * a_bytes;
+  const uint32_t off_w = 0, off_a = w_bytes, off_stg = off_a + PROJ_STAGES * a_bytes, off_bar = off_stg + 2 * PROJ_STG_BYTES;
   const uint32_t sbase = smem_u32(smem);
   auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
   const int W_FULL = 0, A_FULL = 1, A_EMPTY = 5, D_FULL = 9, D_EMPTY = 11;
@@ -759,7 +766,44 @@ __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
       tc_fence_after();
       float* dst = j < p.L ? p.x + p.map.base(s) + (long long)j * p.map.pos_stride : nullptr;
       int c0 = 0;
-      for (; c0 + 64 <= C; c0 += 64) {     // 64 columns per step: 16 residual loads and 2 TMEM loads in flight together
+      if (C % 64 == 0) {
+        uint8_t* stg = smem + off_stg + (size_t)e * PROJ_STG_BYTES;
+        const int wq = warp & 3, sub = lane >> 4, l16 = lane & 15;
+        float* xb = p.x + p.map.base(s);
+        for (; c0 < C; c0 += 64) {
+          {
+            uint32_t r[64];
+            tmem_ld32(lane_addr + e * C + c0, r);
+            tmem_ld32(lane_addr + e * C + c0 + 32, r + 32);
+            tc_wait_ld();
+            uint8_t* row = stg + (size_t)m * PROJ_STG_PITCH;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              *reinterpret_cast<uint4*>(row + 16 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+          // rows wq*32 .. wq*32+31 of the tile, two per instruction, eight instructions in flight
+#pragma unroll 1
+          for (int i0 = 0; i0 < 16; i0 += 8) {
+            float4 xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int jr = jt * 128 + wq * 32 + 2 * (i0 + i) + sub;
+              xv[i] = jr < p.L ? *reinterpret_cast<const float4*>(xb + (long long)jr * p.map.pos_stride + c0 + 4 * l16)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = wq * 32 + 2 * (i0 + i) + sub, jr = jt * 128 + rr;
+              const float4 dv = *reinterpret_cast<const float4*>(stg + (size_t)rr * PROJ_STG_PITCH + 16 * l16);
+              xv[i].x += dv.x; xv[i].y += dv.y; xv[i].z += dv.z; xv[i].w += dv.w;
+              if (jr < p.L) *reinterpret_cast<float4*>(xb + (long long)jr * p.map.pos_stride + c0 + 4 * l16) = xv[i];
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+        }
+      }
+      for (; c0 + 64 <= C; c0 += 64) {     // generic widths: 64 columns per step, row per thread
         uint32_t r[64];
         tmem_ld32(lane_addr + e * C + c0, r);
         tmem_ld32(lane_addr + e * C + c0 + 32, r + 32);

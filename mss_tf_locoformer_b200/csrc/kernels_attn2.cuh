@@ -61,6 +61,13 @@ __device__ __forceinline__ void mma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -345,27 +352,20 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
               l0 *= alpha; l1 *= alpha;
               m_ref = m_new;
             }
-            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float p0 = fast_exp2(__uint_as_float(s[2 * i]) - m_ref);
-              const float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - m_ref);
-              l0 += p0; l1 += p1;
-              pk[i] = pack_bf16(p0, p1);
-            }
-            if (nkh > 16) {
+            for (int c = 0; c < 2; ++c) {                          // 16 keys = one K step of the P.V MMA
+              if (c == 0 || nkh > 16) {
+                uint32_t pk[8];
 #pragma unroll
-              for (int i = 8; i < 16; ++i) {
-                const float p0 = fast_exp2(__uint_as_float(s[2 * i]) - m_ref);
-                const float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - m_ref);
-                l0 += p0; l1 += p1;
-                pk[i] = pack_bf16(p0, p1);
+                for (int i = 0; i < 8; ++i) {
+                  const float p0 = fast_exp2(__uint_as_float(s[16 * c + 2 * i]) - m_ref);
+                  const float p1 = fast_exp2(__uint_as_float(s[16 * c + 2 * i + 1]) - m_ref);
+                  l0 += p0; l1 += p1;
+                  pk[i] = pack_bf16(p0, p1);
+                }
+                tmem_st8(tcol + 64 + h * 16 + c * 8, pk);
               }
-            } else {
-#pragma unroll
-              for (int i = 8; i < 16; ++i) pk[i] = 0u;
             }
-            tmem_st16(tcol + 64 + h * 16, pk);
             tc_wait_st();
           }
           tc_fence_before();

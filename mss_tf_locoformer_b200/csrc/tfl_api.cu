@@ -423,7 +423,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     ProjTcParams pp;
     pp.oimg = oimg; pp.wimg = packed + p.tc_wo; pp.x = x; pp.map = xmap;
     pp.C = C; pp.AP = NPART; pp.L = L; pp.NTL = NTL; pp.n_tiles = nseq * NTL;
-    const uint32_t smem = (uint32_t)NPART * C * 2 + PROJ_STAGES * (uint32_t)NPART * 256 + 256;
+    const uint32_t smem = (uint32_t)NPART * C * 2 + PROJ_STAGES * (uint32_t)NPART * 256 + 2 * PROJ_STG_BYTES + 256;
     if (smem > smem_set[2]) {
       TFL_CUDA(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[2] = smem;
