@@ -20,8 +20,10 @@
 // One persistent CTA per SM; work item = (sequence, group of HG heads, group of QG query tiles), QG * HG = 4:
 // the frequency axis (8 query tiles) runs 4 tiles of one head per item, the time axis (2 tiles) 2 tiles x 2 heads.
 //   warps 0-15    four softmax groups, one query row per thread
-//   warps 16-19   one MMA warp per group: S = Q K^T (64 keys ahead of the softmax), O += P_half V
-//   warp 20       loader: Q tiles (double-buffered per item), K/V ring (one stage = 128 keys of K and V per head)
+//   warps 16-17   one MMA warp per PAIR of groups: S = Q K^T (64 keys ahead of the softmax), O += P_half V
+//   warp 18       loader: Q tiles (double-buffered per item), K/V ring (one stage = 128 keys of K and V per head)
+// (19 warps: at most 5 per SM sub-partition, which is what leaves 96 registers per thread -- with 21 warps the
+// softmax loop spilled its running sums to local memory, 7 % of all instructions issued.)
 // TMEM per group g (128 columns): S [0,64)  P half 0 [64,80)  P half 1 [80,96)  O [96,96+HDP)
 #pragma once
 #include "kernels_attn.cuh"
@@ -40,7 +42,8 @@ struct Attn2Params {
 };
 
 constexpr int ATT2_G = 4;
-constexpr int ATT2_THREADS = 32 * (4 * ATT2_G + ATT2_G + 1);   // softmax warps, MMA warps, loader
+constexpr int ATT2_MMA_WARPS = ATT2_G / 2;                           // one MMA warp per pair of groups
+constexpr int ATT2_THREADS = 32 * (4 * ATT2_G + ATT2_MMA_WARPS + 1);   // softmax warps, MMA warps, loader
 constexpr float ATT2_TH = 16.f;    // raise the softmax reference when a score exceeds it by more than this (log2 units)
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -90,6 +93,68 @@ inline uint32_t attn2_smem(int HDP, int HG, int* NS_out) {
   return fixed + (uint32_t)NS * stage;
 }
 
+// One 32-key half of a score unit for one query row: scores (TMEM) -> max -> [rare: raise m_ref, rescale O] ->
+// exp2 -> bf16 P (TMEM).  NKH = 32: every column is a key of the sequence; otherwise nkh (1..31) columns are.
+template <bool FULL>
+__device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int h, int nkh, bool first, bool last_ld, uint32_t uc,
+                                           int HDP, float& m_ref, float& l0, float& l1) {
+  using namespace tc;
+  constexpr uint32_t S_EMPTY = 8, PV_DONE = 32;                  // byte offsets inside the group's barrier block
+  uint32_t s[32];
+  tmem_ld32(tcol + h * 32, s);
+  tc_wait_ld();
+  if (last_ld) { tc_fence_before(); mbar_arrive(bgrp + S_EMPTY); }   // all scores of the unit are in registers
+  if (!FULL) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i >= nkh) s[i] = 0xff800000u;   // -inf: columns beyond the sequence
+  }
+  float mx[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float t = max3f(__uint_as_float(s[8 * c]), __uint_as_float(s[8 * c + 1]), __uint_as_float(s[8 * c + 2]));
+    t = max3f(t, __uint_as_float(s[8 * c + 3]), __uint_as_float(s[8 * c + 4]));
+    mx[c] = max3f(t, __uint_as_float(s[8 * c + 5]), __uint_as_float(s[8 * c + 6]));
+  }
+  const float mxh = max3f(max3f(mx[0], mx[1], mx[2]), max3f(mx[3], __uint_as_float(s[7]), __uint_as_float(s[15])),
+                          fmaxf(__uint_as_float(s[23]), __uint_as_float(s[31])));
+  if (first) {
+    m_ref = mxh;
+  } else if (__any_sync(0xffffffffu, mxh > m_ref + ATT2_TH)) {
+    // rare: raise the reference and rescale what has been accumulated so far.  Every P.V issued so far must have
+    // landed: the latest one consumed the other half (of this unit for h = 1, of the previous unit for h = 0).
+    const float m_new = mxh > m_ref + ATT2_TH ? mxh : m_ref;
+    const float alpha = fast_exp2(m_ref - m_new);
+    mbar_wait(bgrp + PV_DONE + 8 * (h ^ 1), (h == 1 ? uc : uc - 1) & 1);
+    tc_fence_after();
+    for (int c0 = 0; c0 < HDP; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tcol + 96 + c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+      tmem_st16(tcol + 96 + c0, r);
+    }
+    tc_wait_st();
+    l0 *= alpha; l1 *= alpha;
+    m_ref = m_new;
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {                                  // 16 keys = one K step of the P.V MMA
+    if (FULL || c == 0 || nkh > 16) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float p0 = fast_exp2(__uint_as_float(s[16 * c + 2 * i]) - m_ref);
+        const float p1 = fast_exp2(__uint_as_float(s[16 * c + 2 * i + 1]) - m_ref);
+        l0 += p0; l1 += p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+      tmem_st8(tcol + 64 + h * 16 + c * 8, pk);
+    }
+  }
+  tc_wait_st();
+}
+
 __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p) {
   using namespace tc;
   constexpr int G = ATT2_G;
@@ -102,14 +167,18 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
   const uint32_t off_q = 0, off_kv = 2u * G * tile_bytes, off_bar = off_kv + (uint32_t)NS * stage_bytes;
   const uint32_t sbase = smem_u32(smem);
   auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
-  const int KV_FULL = 0, KV_EMPTY = 8, Q_FULL = 16, Q_EMPTY = 18, S_FULL = 20, S_EMPTY = 24, P_FULL = 28, PV_DONE = 36;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 48);
+  // barrier slots: ring 0..15, Q 16..19, then one block of 8 per group (so a group's barriers are base + constant):
+  //   +0 S_FULL  +1 S_EMPTY  +2,+3 P_FULL[half]  +4,+5 PV_DONE[half]
+  const int KV_FULL = 0, KV_EMPTY = 8, Q_FULL = 16, Q_EMPTY = 18, GRP = 20;
+  constexpr uint32_t S_FULL = 0, S_EMPTY = 8, P_FULL = 16, PV_DONE = 32;      // byte offsets inside a group block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * (GRP + 8 * G));
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), G); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), G); }
+    for (int i = 0; i < NS; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), ATT2_MMA_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), ATT2_MMA_WARPS); }
     for (int g = 0; g < G; ++g) {
-      mbar_init(BAR(S_FULL + g), 1); mbar_init(BAR(S_EMPTY + g), 128);
-      for (int h = 0; h < 2; ++h) { mbar_init(BAR(P_FULL + g * 2 + h), 128); mbar_init(BAR(PV_DONE + g * 2 + h), 1); }
+      const uint32_t bg = BAR(GRP + 8 * g);
+      mbar_init(bg + S_FULL, 1); mbar_init(bg + S_EMPTY, 128);
+      for (int h = 0; h < 2; ++h) { mbar_init(bg + P_FULL + 8 * h, 128); mbar_init(bg + PV_DONE + 8 * h, 1); }
     }
     fence_barrier_init();
   }
@@ -121,14 +190,16 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
   const size_t which_stride = (size_t)p.nseq * p.heads * NTL * HDP * 128;   // elements between the q, k, v planes
   const int n_last = p.L - (NU - 1) * 64;                                   // keys in the last unit (1..64)
 
-  // item -> (sequence, first head, first query tile); group g -> (head, tile)
+  // item -> (sequence, first head, first query tile); group g -> (head, tile).  Groups 2k and 2k+1 form a PAIR served
+  // by one MMA warp in lock step; a pair runs the whole protocol when its first group has work (a second group
+  // without work -- ragged tile / head counts -- computes on whatever its buffers hold and stores nothing).
   auto decode = [&](int item, int& seq, int& h0, int& q0) {
     const int qg = item % p.NQG, t = item / p.NQG;
     q0 = qg * QG; h0 = (t % p.NHG) * HG; seq = t / p.NHG;
   };
   auto group_active = [&](int g, int h0, int q0) { return h0 + g / QG < p.heads && q0 + g % QG < p.NQT; };
 
-  if (warp == 5 * G) {
+  if (warp == 4 * G + ATT2_MMA_WARPS) {
     // ===================== loader =====================
     uint32_t kslot = 0, kph = 0, qph = 0;
     int n_local = 0;
@@ -167,13 +238,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
       }
     }
   } else if (warp >= 4 * G) {
-    // ===================== MMA warp of group g =====================
-    // S for unit u+1 (or unit 0 of the next item) is issued between the two P.V halves of unit u, so a softmax
-    // group finds its next scores in TMEM when it gets there.  The whole warp runs the control flow; one elected
-    // lane issues.
-    const int g = warp - 4 * G;
-    const int hh = g / QG;                                         // head slot of this group inside a K/V stage
-    const uint32_t tcol = tmem + g * 128;
+    // ===================== MMA warp of the group pair (2 pw, 2 pw + 1) =====================
+    // Per unit and group: O (+)= P[half 0] V, then S of the next unit (or of unit 0 of the next item), then
+    // O += P[half 1] V -- so a softmax group finds its next scores in TMEM when it gets there.  The whole warp runs the
+    // control flow; one elected lane issues.
+    const int pw = warp - 4 * G;
     const uint32_t idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
     const uint32_t idesc_s_full = instr_desc(128, 64), idesc_s_last = instr_desc(128, (n_last + 15) & ~15);
     const uint32_t hi_k = (128u >> 4) | (1u << 14);              // K-major tiles: SBO = 128 B
@@ -185,18 +254,38 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
     uint32_t kslot = 0, kph = 0, qph = 0;
     uint32_t us = 0, up = 0;                                       // running unit counters: S issued, P.V consumed
     auto issue_s = [&](int b, uint32_t slot, int half, bool last_unit, bool last_of_item) {
-      mbar_wait(BAR(S_EMPTY + g), (us & 1) ^ 1);
-      ++us;
-      tc_fence_after();
-      const uint32_t qa = q16 + (b * G + g) * tile16, kb = kv16 + slot * stage16 + hh * 2 * tile16 + half * 64;
       const uint32_t idesc = last_unit ? idesc_s_last : idesc_s_full;
-      if (elect_one()) {
-        for (int kk = 0; kk < HDP / 16; ++kk)
-          mma_lohi(tcol, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc, (uint32_t)kk);
-        mma_commit(BAR(S_FULL + g));
-        if (last_of_item) mma_commit(BAR(Q_EMPTY + b));
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g = 2 * pw + gi;
+        mbar_wait(BAR(GRP + 8 * g) + S_EMPTY, (us & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qa = q16 + (b * G + g) * tile16, kb = kv16 + slot * stage16 + (g / QG) * 2 * tile16 + half * 64;
+        if (elect_one()) {
+          for (int kk = 0; kk < HDP / 16; ++kk)
+            mma_lohi(tmem + g * 128, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc, (uint32_t)kk);
+          mma_commit(BAR(GRP + 8 * g) + S_FULL);
+          if (last_of_item && gi == 1) mma_commit(BAR(Q_EMPTY + b));
+        }
+        __syncwarp();
       }
-      __syncwarp();
+      ++us;
+    };
+    auto issue_pv = [&](int h, int n_steps, uint32_t vrow16, bool fresh) {
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g = 2 * pw + gi;
+        const uint32_t bg = BAR(GRP + 8 * g), tcol = tmem + g * 128;
+        mbar_wait(bg + P_FULL + 8 * h, up & 1);
+        tc_fence_after();
+        const uint32_t vb = vrow16 + (g / QG) * 2 * tile16;
+        if (elect_one()) {
+          for (int c = 0; c < n_steps; ++c)
+            mma_ts_lohi(tcol + 96, tcol + 64 + h * 16 + c * 8, (vb + c * 16) | lo_v, hi_v, idesc_pv, (uint32_t)(!fresh || c > 0));
+          mma_commit(bg + PV_DONE + 8 * h);
+        }
+        __syncwarp();
+      }
     };
     auto wait_q = [&](int b) {
       mbar_wait(BAR(Q_FULL + b), (qph >> b) & 1);
@@ -213,25 +302,25 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
       __syncwarp();
       if (++kslot == (uint32_t)NS) { kslot = 0; kph ^= 1; }
     };
-    auto item_active = [&](int item) {
+    auto pair_active = [&](int item) {
       if (item >= p.n_items) return false;
       int seq, h0, q0;
       decode(item, seq, h0, q0);
-      return group_active(g, h0, q0);
+      return group_active(2 * pw, h0, q0);
     };
     int n_local = 0;
-    if (item_active(blockIdx.x)) {                                 // S of the very first unit
+    if (pair_active(blockIdx.x)) {                                 // S of the very first unit
       wait_q(0);
       mbar_wait(BAR(KV_FULL + kslot), kph);
       tc_fence_after();
       issue_s(0, kslot, 0, NU == 1, NU == 1);
     }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
-      const bool active = item_active(item);
+      const bool active = pair_active(item);
       const int b = n_local & 1;
-      const bool next_active = item_active(item + gridDim.x);
+      const bool next_active = pair_active(item + gridDim.x);
       if (!active) {
-        // no work for this group in the item: keep the ring / Q protocols alive (their barriers expect one arrival
+        // no work for this pair in the item: keep the ring / Q protocols alive (their barriers expect one arrival
         // per MMA warp) and pre-issue S for the next item after the last stage
         wait_q(b);
         if (elect_one()) mbar_arrive(BAR(Q_EMPTY + b));
@@ -256,17 +345,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
         next_slot(nslot, nph);
         const int nk = min(64, p.L - u * 64);
         const int nch = (nk + 15) >> 4, nch0 = min(nch, 2), nch1 = nch - nch0;    // 16-key MMA steps per half
-        const uint32_t vb = kv16 + kslot * stage16 + hh * 2 * tile16 + tile16 + half * 64;
-        // ---- O (+)= P[half 0] . V ----
-        mbar_wait(BAR(P_FULL + g * 2), up & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          for (int c = 0; c < nch0; ++c)
-            mma_ts_lohi(tcol + 96, tcol + 64 + c * 8, (vb + c * 16) | lo_v, hi_v, idesc_pv, (uint32_t)(u | c));
-          mma_commit(BAR(PV_DONE + g * 2));
-        }
-        __syncwarp();
-        // ---- S for the next unit ----
+        const uint32_t vrow16 = kv16 + kslot * stage16 + tile16 + half * 64;      // V rows of this unit (head slot 0)
+        issue_pv(0, nch0, vrow16, u == 0);
         if (u + 1 < NU) {
           if (half == 1) { mbar_wait(BAR(KV_FULL + nslot), nph); tc_fence_after(); }
           issue_s(b, half == 1 ? nslot : kslot, half ^ 1, u + 2 == NU, u + 2 == NU);
@@ -276,17 +356,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
           tc_fence_after();
           issue_s(b ^ 1, nslot, 0, NU == 1, NU == 1);
         }
-        // ---- O += P[half 1] . V ----
-        mbar_wait(BAR(P_FULL + g * 2 + 1), up & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          for (int c = 0; c < nch1; ++c)
-            mma_ts_lohi(tcol + 96, tcol + 80 + c * 8, (vb + (2 + c) * 16) | lo_v, hi_v, idesc_pv, 1u);
-          mma_commit(BAR(PV_DONE + g * 2 + 1));
-        }
-        __syncwarp();
+        issue_pv(1, nch1, vrow16 + 32, false);
         ++up;
-        if (half == 1 || u + 1 == NU) release_kv(true);            // this group is done with the K/V stage
+        if (half == 1 || u + 1 == NU) release_kv(true);            // this pair is done with the K/V stage
       }
     }
   } else {
@@ -295,100 +367,64 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
     const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;
     const uint32_t tcol = tmem + ((uint32_t)(quarter * 32) << 16) + g * 128;
+    const uint32_t bgrp = BAR(GRP + 8 * g);
     const int OC = HDP / 8;
     uint32_t uc = 0;                                               // running unit counter of this group
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int seq, h0, q0;
       decode(item, seq, h0, q0);
-      if (!group_active(g, h0, q0)) continue;
+      if (!group_active(g & ~1, h0, q0)) continue;                 // the pair has no work in this item
+      const bool store = group_active(g, h0, q0);
       const int head = h0 + g / QG, qt = q0 + g % QG;
       float m_ref = 0.f, l0 = 0.f, l1 = 0.f;
-      for (int u = 0; u < NU; ++u, ++uc) {
-        const int nk = min(64, p.L - u * 64);
-        mbar_wait(BAR(S_FULL + g), uc & 1);
+      // ---- full 64-key units ----
+      const int n_full = n_last == 64 ? NU : NU - 1;
+      for (int u = 0; u < n_full; ++u, ++uc) {
+        mbar_wait(bgrp + S_FULL, uc & 1);
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int nkh = min(32, nk - 32 * h);                    // valid keys in this half (<= 0: empty)
-          // P[h] is free once P.V of the previous unit's half h has completed.  Waited for in EVERY half, also the
-          // empty ones: a parity wait is only meaningful for the phase right after the last one this thread has seen.
-          if (uc > 0) { mbar_wait(BAR(PV_DONE + g * 2 + h), (uc - 1) & 1); tc_fence_after(); }
-          if (nkh > 0) {
-            uint32_t s[32];
-            tmem_ld32(tcol + h * 32, s);
-            tc_wait_ld();
-            if (h == 1 || nk <= 32) { tc_fence_before(); mbar_arrive(BAR(S_EMPTY + g)); }   // scores are in registers
-            if (nkh < 32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (i >= nkh) s[i] = 0xff800000u;   // -inf: columns beyond the sequence
-            }
-            float mx[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float t = max3f(__uint_as_float(s[8 * c]), __uint_as_float(s[8 * c + 1]), __uint_as_float(s[8 * c + 2]));
-              t = max3f(t, __uint_as_float(s[8 * c + 3]), __uint_as_float(s[8 * c + 4]));
-              mx[c] = max3f(t, __uint_as_float(s[8 * c + 5]), __uint_as_float(s[8 * c + 6]));
-            }
-            const float mxh = max3f(max3f(mx[0], mx[1], mx[2]), max3f(mx[3], __uint_as_float(s[7]), __uint_as_float(s[15])),
-                                    fmaxf(__uint_as_float(s[23]), __uint_as_float(s[31])));
-            if (u == 0 && h == 0) {
-              m_ref = mxh;
-            } else if (__any_sync(0xffffffffu, mxh > m_ref + ATT2_TH)) {
-              // rare: raise the reference and rescale what has been accumulated so far.  Every P.V issued so far must
-              // have landed: the latest one consumed the other half (of this unit for h = 1, of the previous for h = 0).
-              const float m_new = mxh > m_ref + ATT2_TH ? mxh : m_ref;
-              const float alpha = fast_exp2(m_ref - m_new);
-              mbar_wait(BAR(PV_DONE + g * 2 + (h ^ 1)), (h == 1 ? uc : uc - 1) & 1);
-              tc_fence_after();
-              for (int c0 = 0; c0 < HDP; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tcol + 96 + c0, r);
-                tc_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-                tmem_st16(tcol + 96 + c0, r);
-              }
-              tc_wait_st();
-              l0 *= alpha; l1 *= alpha;
-              m_ref = m_new;
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {                          // 16 keys = one K step of the P.V MMA
-              if (c == 0 || nkh > 16) {
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float p0 = fast_exp2(__uint_as_float(s[16 * c + 2 * i]) - m_ref);
-                  const float p1 = fast_exp2(__uint_as_float(s[16 * c + 2 * i + 1]) - m_ref);
-                  l0 += p0; l1 += p1;
-                  pk[i] = pack_bf16(p0, p1);
-                }
-                tmem_st8(tcol + 64 + h * 16 + c * 8, pk);
-              }
-            }
-            tc_wait_st();
-          }
+          // P[h] is free once P.V of the previous unit's half h has completed.  Waited for in EVERY half of every
+          // unit: a parity wait is only meaningful for the phase right after the last one this thread has seen.
+          if (uc > 0) { mbar_wait(bgrp + PV_DONE + 8 * h, (uc - 1) & 1); tc_fence_after(); }
+          attn2_half<true>(tcol, bgrp, h, 32, u == 0 && h == 0, h == 1, uc, HDP, m_ref, l0, l1);
           tc_fence_before();
-          mbar_arrive(BAR(P_FULL + g * 2 + h));
+          mbar_arrive(bgrp + P_FULL + 8 * h);
         }
       }
+      // ---- the short last unit (n_last < 64 keys) ----
+      if (n_full < NU) {
+        mbar_wait(bgrp + S_FULL, uc & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int nkh = min(32, n_last - 32 * h);
+          if (uc > 0) { mbar_wait(bgrp + PV_DONE + 8 * h, (uc - 1) & 1); tc_fence_after(); }
+          if (nkh > 0) attn2_half<false>(tcol, bgrp, h, nkh, n_full == 0 && h == 0, h == 1 || n_last <= 32, uc, HDP, m_ref, l0, l1);
+          tc_fence_before();
+          mbar_arrive(bgrp + P_FULL + 8 * h);
+        }
+        ++uc;
+      }
       // ---- all keys done: O / l -> this head's slice of the o image ----
-      mbar_wait(BAR(PV_DONE + g * 2 + 1), (uc - 1) & 1);
+      mbar_wait(bgrp + PV_DONE + 8, (uc - 1) & 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld16(tcol + 96, r);
       if (HDP > 16) tmem_ld16(tcol + 96 + 16, r + 16);
       tc_wait_ld();
-      const float inv = 1.f / (l0 + l1);
-      __nv_bfloat16* ob = p.o + (((size_t)seq * NTL + qt) * (p.heads * OC) + (size_t)head * OC) * 1024 + (size_t)m * 8;
+      if (store) {
+        const float inv = 1.f / (l0 + l1);
+        __nv_bfloat16* ob = p.o + (((size_t)seq * NTL + qt) * (p.heads * OC) + (size_t)head * OC) * 1024 + (size_t)m * 8;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < OC) {
-          uint32_t w[4];
+        for (int c = 0; c < 4; ++c) {
+          if (c < OC) {
+            uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            w[e] = pack_bf16(__uint_as_float(r[c * 8 + 2 * e]) * inv, __uint_as_float(r[c * 8 + 2 * e + 1]) * inv);
-          *reinterpret_cast<uint4*>(ob + (size_t)c * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int e = 0; e < 4; ++e)
+              w[e] = pack_bf16(__uint_as_float(r[c * 8 + 2 * e]) * inv, __uint_as_float(r[c * 8 + 2 * e + 1]) * inv);
+            *reinterpret_cast<uint4*>(ob + (size_t)c * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
     }
