@@ -10,12 +10,14 @@
 //     reference m_ref is the row maximum of the first 32 keys and is only raised -- with a rescale of the TMEM
 //     accumulator by the softmax thread itself -- when a later score exceeds it by more than 2^ATT2_TH
 //     (bf16 / fp32 share an 8-bit exponent: a stale reference costs range, not precision);
-//   * scores are consumed in halves of 32 keys (one tcgen05.ld, one max3 tree, 32 exp2, one tcgen05.st), each half
-//     published separately, so a thread holds 32 + 16 registers of tile data and FOUR softmax groups (16 warps,
-//     4 per SM sub-partition) fit next to the MMA warps -- enough warps in flight to keep the exp2 unit busy while
-//     others wait on TMEM loads or barriers;
-//   * the key range ends in a unit of N = ceil16(remaining keys) columns instead of a masked 64-key unit
-//     (1025 = 16*64 + 1, 259 = 4*64 + 3).
+//   * the work unit is a HALF of 32 keys (S = M128 x N32, one tcgen05.ld, one max3 tree, 32 exp2, tcgen05.st), so a
+//     thread holds 32 + 8 registers of tile data and FOUR softmax groups (16 warps, 4 per SM sub-partition) fit --
+//     enough warps in flight to keep the exp2 unit busy while others wait on TMEM loads or barriers;
+//   * S, P share three rotating 32-column TMEM buffers per group: P_k overwrites the first 16 columns of the buffer
+//     S_k was read from, and S_{k+3} is issued into it right behind P_k V_k (MMAs execute in issue order).  Scores
+//     are therefore produced three halves ahead of their use: no softmax warp ever waits for the tensor pipe, and
+//     the four warps of a group need not run in lock step;
+//   * the key range ends in a half of N = ceil16(remaining keys) columns (1025 = 32*32 + 1, 259 = 8*32 + 3).
 //
 // One persistent CTA per SM; work item = (sequence, group of HG heads, group of QG query tiles), QG * HG = 4:
 // the frequency axis (8 query tiles) runs 4 tiles of one head per item, the time axis (2 tiles) 2 tiles x 2 heads.
@@ -24,7 +26,7 @@
 //   warp 18       loader: Q tiles (double-buffered per item), K/V ring (one stage = 128 keys of K and V per head)
 // (19 warps: at most 5 per SM sub-partition, which is what leaves 96 registers per thread -- with 21 warps the
 // softmax loop spilled its running sums to local memory, 7 % of all instructions issued.)
-// TMEM per group g (128 columns): S [0,64)  P half 0 [64,80)  P half 1 [80,96)  O [96,96+HDP)
+// TMEM per group g (128 columns): three S/P buffers [0,32) [32,64) [64,96), O [96,96+HDP)
 #pragma once
 #include "kernels_attn.cuh"
 
@@ -34,7 +36,6 @@ struct Attn2Params {
   const __nv_bfloat16* qkv; __nv_bfloat16* o;
   int nseq, heads, L, NTL, HDP;
   int NQT;       // full query tiles handled here (trailing rows may go to attn_tail_rows_kernel)
-  int NU;        // 64-key units per sequence (the last one may be short)
   int QG, HG;    // query tiles / heads per work item
   int NQG, NHG;  // query-tile groups / head groups per sequence
   int NS;        // K/V ring stages
@@ -85,7 +86,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 
 inline uint32_t attn2_smem(int HDP, int HG, int* NS_out) {
   const uint32_t tile = (uint32_t)HDP * 128 * 2;
-  const uint32_t fixed = 2u * ATT2_G * tile + 512;
+  const uint32_t fixed = 2u * ATT2_G * tile + 1024;
   const uint32_t stage = (uint32_t)HG * 2 * tile;
   int NS = (int)((TC_SMEM_MAX - fixed) / stage);
   if (NS > 8) NS = 8;
@@ -93,17 +94,16 @@ inline uint32_t attn2_smem(int HDP, int HG, int* NS_out) {
   return fixed + (uint32_t)NS * stage;
 }
 
-// One 32-key half of a score unit for one query row: scores (TMEM) -> max -> [rare: raise m_ref, rescale O] ->
-// exp2 -> bf16 P (TMEM).  NKH = 32: every column is a key of the sequence; otherwise nkh (1..31) columns are.
+// One 32-key half for one query row: scores (TMEM buffer bb) -> max -> [rare: raise m_ref, rescale O] -> exp2 ->
+// bf16 P written over the first 16 columns of the same buffer.  FULL: all 32 columns are keys; otherwise nkh are.
 template <bool FULL>
-__device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int h, int nkh, bool first, bool last_ld, uint32_t uc,
+__device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int bb, uint32_t ph, uint32_t kk, int nkh, bool first,
                                            int HDP, float& m_ref, float& l0, float& l1) {
   using namespace tc;
-  constexpr uint32_t S_EMPTY = 8, PV_DONE = 32;                  // byte offsets inside the group's barrier block
+  constexpr uint32_t PV_DONE = 48;                               // byte offset inside the group's barrier block
   uint32_t s[32];
-  tmem_ld32(tcol + h * 32, s);
+  tmem_ld32(tcol + bb * 32, s);
   tc_wait_ld();
-  if (last_ld) { tc_fence_before(); mbar_arrive(bgrp + S_EMPTY); }   // all scores of the unit are in registers
   if (!FULL) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) if (i >= nkh) s[i] = 0xff800000u;   // -inf: columns beyond the sequence
@@ -121,10 +121,11 @@ __device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int h, 
     m_ref = mxh;
   } else if (__any_sync(0xffffffffu, mxh > m_ref + ATT2_TH)) {
     // rare: raise the reference and rescale what has been accumulated so far.  Every P.V issued so far must have
-    // landed: the latest one consumed the other half (of this unit for h = 1, of the previous unit for h = 0).
+    // landed; MMAs complete in issue order, so it is enough to wait for the one of the previous half.
     const float m_new = mxh > m_ref + ATT2_TH ? mxh : m_ref;
     const float alpha = fast_exp2(m_ref - m_new);
-    mbar_wait(bgrp + PV_DONE + 8 * (h ^ 1), (h == 1 ? uc : uc - 1) & 1);
+    const int pb = bb == 0 ? 2 : bb - 1;
+    mbar_wait(bgrp + PV_DONE + 8 * pb, bb == 0 ? ph ^ 1 : ph);
     tc_fence_after();
     for (int c0 = 0; c0 < HDP; c0 += 16) {
       uint32_t r[16];
@@ -138,6 +139,9 @@ __device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int h, 
     l0 *= alpha; l1 *= alpha;
     m_ref = m_new;
   }
+  // Phase bookkeeping only (S of this half was issued after P.V of half kk-3, so that one has long completed): a
+  // parity wait is only meaningful for the phase right after the last one this thread has observed.
+  if (kk >= 3) mbar_wait(bgrp + PV_DONE + 8 * bb, ph ^ 1);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {                                  // 16 keys = one K step of the P.V MMA
     if (FULL || c == 0 || nkh > 16) {
@@ -149,36 +153,38 @@ __device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int h, 
         l0 += p0; l1 += p1;
         pk[i] = pack_bf16(p0, p1);
       }
-      tmem_st8(tcol + 64 + h * 16 + c * 8, pk);
+      tmem_st8(tcol + bb * 32 + c * 8, pk);
     }
   }
   tc_wait_st();
 }
 
+template <int KS>   // K steps of S = Q K^T (head_dim padded to 16 * KS)
 __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p) {
   using namespace tc;
   constexpr int G = ATT2_G;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HDP = p.HDP, NTL = p.NTL, NU = p.NU, QG = p.QG, HG = p.HG, NS = p.NS;
-  const int NST = (NU + 1) / 2;                                  // K/V ring stages (128 keys) per item
+  const int HDP = p.HDP, NTL = p.NTL, QG = p.QG, HG = p.HG, NS = p.NS;
+  const int NH = (p.L + 31) / 32;                                // 32-key halves per sequence
+  const int NST = NTL;                                           // K/V ring stages (128 keys) per item
+  const int n_last = p.L - (NH - 1) * 32;                        // keys in the last half (1..32)
   const uint32_t tile_bytes = (uint32_t)HDP * 128 * 2;          // one Q / K / V tile (128 rows)
   const uint32_t stage_bytes = (uint32_t)HG * 2 * tile_bytes;   // per head: K tile, V tile
   const uint32_t off_q = 0, off_kv = 2u * G * tile_bytes, off_bar = off_kv + (uint32_t)NS * stage_bytes;
   const uint32_t sbase = smem_u32(smem);
   auto BAR = [&](int i) { return sbase + off_bar + 8u * i; };
-  // barrier slots: ring 0..15, Q 16..19, then one block of 8 per group (so a group's barriers are base + constant):
-  //   +0 S_FULL  +1 S_EMPTY  +2,+3 P_FULL[half]  +4,+5 PV_DONE[half]
+  // barrier slots: ring 0..15, Q 16..19, then one block of 16 per group (a group's barriers are base + constant):
+  //   +0..2 S_FULL[buffer]  +3..5 P_FULL[buffer]  +6..8 PV_DONE[buffer]
   const int KV_FULL = 0, KV_EMPTY = 8, Q_FULL = 16, Q_EMPTY = 18, GRP = 20;
-  constexpr uint32_t S_FULL = 0, S_EMPTY = 8, P_FULL = 16, PV_DONE = 32;      // byte offsets inside a group block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * (GRP + 8 * G));
+  constexpr uint32_t S_FULL = 0, P_FULL = 24, PV_DONE = 48;      // byte offsets inside a group block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * (GRP + 16 * G));
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(BAR(KV_FULL + i), 1); mbar_init(BAR(KV_EMPTY + i), ATT2_MMA_WARPS); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), ATT2_MMA_WARPS); }
     for (int g = 0; g < G; ++g) {
-      const uint32_t bg = BAR(GRP + 8 * g);
-      mbar_init(bg + S_FULL, 1); mbar_init(bg + S_EMPTY, 128);
-      for (int h = 0; h < 2; ++h) { mbar_init(bg + P_FULL + 8 * h, 128); mbar_init(bg + PV_DONE + 8 * h, 1); }
+      const uint32_t bg = BAR(GRP + 16 * g);
+      for (int i = 0; i < 3; ++i) { mbar_init(bg + S_FULL + 8 * i, 1); mbar_init(bg + P_FULL + 8 * i, 128); mbar_init(bg + PV_DONE + 8 * i, 1); }
     }
     fence_barrier_init();
   }
@@ -188,11 +194,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const size_t which_stride = (size_t)p.nseq * p.heads * NTL * HDP * 128;   // elements between the q, k, v planes
-  const int n_last = p.L - (NU - 1) * 64;                                   // keys in the last unit (1..64)
 
   // item -> (sequence, first head, first query tile); group g -> (head, tile).  Groups 2k and 2k+1 form a PAIR served
-  // by one MMA warp in lock step; a pair runs the whole protocol when its first group has work (a second group
-  // without work -- ragged tile / head counts -- computes on whatever its buffers hold and stores nothing).
+  // by one MMA warp; a pair runs the whole protocol when its first group has work (a second group without work --
+  // ragged tile / head counts -- computes on whatever its buffers hold and stores nothing).
   auto decode = [&](int item, int& seq, int& h0, int& q0) {
     const int qg = item % p.NQG, t = item / p.NQG;
     q0 = qg * QG; h0 = (t % p.NHG) * HG; seq = t / p.NHG;
@@ -239,126 +244,143 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
     }
   } else if (warp >= 4 * G) {
     // ===================== MMA warp of the group pair (2 pw, 2 pw + 1) =====================
-    // Per unit and group: O (+)= P[half 0] V, then S of the next unit (or of unit 0 of the next item), then
-    // O += P[half 1] V -- so a softmax group finds its next scores in TMEM when it gets there.  The whole warp runs the
-    // control flow; one elected lane issues.
+    // Two cursors over the halves of this pair's items.  The P.V cursor follows the softmax groups (O (+)= P_k V_k as
+    // soon as P_k is published); the S cursor runs THREE halves ahead (S_{k+3} = Q K_{k+3}^T is issued right after
+    // P_k V_k into the TMEM buffer that P_k occupies -- MMAs of one thread execute in issue order, so the overwrite
+    // is safe), across item boundaries.  A softmax warp therefore always has its next scores waiting, and the four
+    // warps of a group may drift up to two halves apart.  The whole warp runs the control flow; one lane issues.
     const int pw = warp - 4 * G;
     const uint32_t idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
-    const uint32_t idesc_s_full = instr_desc(128, 64), idesc_s_last = instr_desc(128, (n_last + 15) & ~15);
+    const uint32_t idesc_s_full = instr_desc(128, 32), idesc_s_last = instr_desc(128, (n_last + 15) & ~15);
     const uint32_t hi_k = (128u >> 4) | (1u << 14);              // K-major tiles: SBO = 128 B
     const uint32_t lo_k = 128u << 16;                            //   128-row tiles: LBO = 128 rows * 16 B
     const uint32_t hi_v = ((128u * 16) >> 4) | (1u << 14);       // V as MN-major: SBO = 2048 B (next 8 columns)
     const uint32_t lo_v = (128u >> 4) << 16;                     //                LBO = 128 B (next 8 kv rows)
-    const uint32_t q16 = (sbase + off_q) >> 4, kv16 = (sbase + off_kv) >> 4;
+    const uint32_t kv16 = (sbase + off_kv) >> 4;
     const uint32_t tile16 = tile_bytes >> 4, stage16 = stage_bytes >> 4;
-    uint32_t kslot = 0, kph = 0, qph = 0;
-    uint32_t us = 0, up = 0;                                       // running unit counters: S issued, P.V consumed
-    auto issue_s = [&](int b, uint32_t slot, int half, bool last_unit, bool last_of_item) {
-      const uint32_t idesc = last_unit ? idesc_s_last : idesc_s_full;
-#pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int g = 2 * pw + gi;
-        mbar_wait(BAR(GRP + 8 * g) + S_EMPTY, (us & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qa = q16 + (b * G + g) * tile16, kb = kv16 + slot * stage16 + (g / QG) * 2 * tile16 + half * 64;
-        if (elect_one()) {
-          for (int kk = 0; kk < HDP / 16; ++kk)
-            mma_lohi(tmem + g * 128, (qa + kk * 2 * 128) | lo_k, hi_k, (kb + kk * 2 * 128) | lo_k, hi_k, idesc, (uint32_t)kk);
-          mma_commit(BAR(GRP + 8 * g) + S_FULL);
-          if (last_of_item && gi == 1) mma_commit(BAR(Q_EMPTY + b));
-        }
-        __syncwarp();
+    const int pv_last_steps = (n_last + 15) >> 4;
+    // everything that depends only on the group, once (this loop body runs ~10^4 times per CTA: keep it lean)
+    const uint32_t bg0 = BAR(GRP + 16 * (2 * pw)), bg1 = bg0 + 16 * 8;
+    const uint32_t tc0 = tmem + (2 * pw) * 128, tc1 = tc0 + 128;
+    const uint32_t hs0 = (uint32_t)((2 * pw) / QG) * 2 * tile16, hs1 = (uint32_t)((2 * pw + 1) / QG) * 2 * tile16;
+    const uint32_t qt0 = ((sbase + off_q) >> 4) + (2 * pw) * tile16;   // Q tile of group 0 in buffer 0 (16-byte units)
+    auto pair_active = [&](int item) {
+      int seq, h0, q0;
+      decode(item, seq, h0, q0);
+      return group_active(2 * pw, h0, q0);
+    };
+    // ---- S cursor ----
+    int s_item = blockIdx.x, s_nl = 0, s_k = 0, s_kq = 0;          // item, its local index, half in the item, half in the stage
+    uint32_t s_slot = 0, s_ph = 0, s_bb = 0;                       // ring slot / phase of the half's stage; TMEM buffer
+    uint32_t s_q16 = 0, s_st16 = 0;                                // Q tile (group 0) and stage base of the cursor
+    int lead = 0;                                                  // halves the S cursor is ahead of the P.V cursor
+    int s_stage = 0, pv_stage = 0;                                 // running stage counters of the two cursors
+    // S of the cursor's half, in three steps so that the P.V loop can issue it inside its own elected block:
+    // s_prepare (waits; false = parked or nothing left), s_emit (MMAs + commits, elected lane only), s_advance.
+    auto s_prepare = [&]() -> bool {
+      if (s_k == 0) {
+        // entering an item.  The cursor never runs past an item this pair has no work in (it parks there until the
+        // P.V cursor has done that item's ring / Q bookkeeping): every barrier phase is then observed in order by
+        // exactly one of the two cursors, and the ring can never be waited on deeper than it is.
+        if (s_item >= p.n_items || !pair_active(s_item)) return false;
+        mbar_wait(BAR(Q_FULL + (s_nl & 1)), (uint32_t)(s_nl >> 1) & 1);
+        s_q16 = qt0 + (s_nl & 1) * G * tile16;
       }
-      ++us;
-    };
-    auto issue_pv = [&](int h, int n_steps, uint32_t vrow16, bool fresh) {
-#pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int g = 2 * pw + gi;
-        const uint32_t bg = BAR(GRP + 8 * g), tcol = tmem + g * 128;
-        mbar_wait(bg + P_FULL + 8 * h, up & 1);
-        tc_fence_after();
-        const uint32_t vb = vrow16 + (g / QG) * 2 * tile16;
-        if (elect_one()) {
-          for (int c = 0; c < n_steps; ++c)
-            mma_ts_lohi(tcol + 96, tcol + 64 + h * 16 + c * 8, (vb + c * 16) | lo_v, hi_v, idesc_pv, (uint32_t)(!fresh || c > 0));
-          mma_commit(bg + PV_DONE + 8 * h);
-        }
-        __syncwarp();
+      if (s_kq == 0) {
+        if (s_stage - pv_stage >= NS) return false;                // that ring slot still holds a stage the P.V cursor needs
+        mbar_wait(BAR(KV_FULL + s_slot), s_ph);
+        s_st16 = kv16 + s_slot * stage16;
       }
+      return true;
     };
-    auto wait_q = [&](int b) {
-      mbar_wait(BAR(Q_FULL + b), (qph >> b) & 1);
-      qph ^= 1u << b;
+    auto s_emit = [&]() {
+      const bool last = s_k == NH - 1;
+      const uint32_t idesc = last ? idesc_s_last : idesc_s_full;
+      const uint32_t kb = s_st16 + s_kq * 32, d = s_bb * 32;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk)
+        mma_lohi(tc0 + d, (s_q16 + kk * 256) | lo_k, hi_k, (kb + hs0 + kk * 256) | lo_k, hi_k, idesc, (uint32_t)kk);
+      mma_commit(bg0 + S_FULL + 8 * s_bb);
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk)
+        mma_lohi(tc1 + d, (s_q16 + tile16 + kk * 256) | lo_k, hi_k, (kb + hs1 + kk * 256) | lo_k, hi_k, idesc, (uint32_t)kk);
+      mma_commit(bg1 + S_FULL + 8 * s_bb);
+      if (last) mma_commit(BAR(Q_EMPTY + (s_nl & 1)));             // all S of the item issued: its Q tiles are free after
     };
-    auto next_slot = [&](uint32_t& nslot, uint32_t& nph) {
-      nslot = kslot + 1; nph = kph;
-      if (nslot == (uint32_t)NS) { nslot = 0; nph ^= 1; }
+    auto s_advance = [&]() {
+      s_bb = s_bb == 2 ? 0 : s_bb + 1;
+      ++s_k; ++lead;
+      s_kq = (s_kq + 1) & 3;
+      if (s_k == NH) { s_k = 0; s_kq = 0; s_item += gridDim.x; ++s_nl; }
+      if (s_kq == 0) { ++s_stage; if (++s_slot == (uint32_t)NS) { s_slot = 0; s_ph ^= 1; } }
     };
+    auto issue_next_s = [&]() -> bool {
+      if (!s_prepare()) return false;
+      tc_fence_after();
+      if (elect_one()) s_emit();
+      __syncwarp();
+      s_advance();
+      return true;
+    };
+    // ---- P.V cursor ----
+    uint32_t kslot = 0, kph = 0;
+    uint32_t bb = 0, bph = 0;                                      // TMEM buffer of the current half and its phase
     auto release_kv = [&](bool by_commit) {
       if (elect_one()) {
         if (by_commit) mma_commit(BAR(KV_EMPTY + kslot)); else mbar_arrive(BAR(KV_EMPTY + kslot));
       }
       __syncwarp();
+      ++pv_stage;
       if (++kslot == (uint32_t)NS) { kslot = 0; kph ^= 1; }
     };
-    auto pair_active = [&](int item) {
-      if (item >= p.n_items) return false;
-      int seq, h0, q0;
-      decode(item, seq, h0, q0);
-      return group_active(2 * pw, h0, q0);
-    };
     int n_local = 0;
-    if (pair_active(blockIdx.x)) {                                 // S of the very first unit
-      wait_q(0);
-      mbar_wait(BAR(KV_FULL + kslot), kph);
-      tc_fence_after();
-      issue_s(0, kslot, 0, NU == 1, NU == 1);
-    }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
-      const bool active = pair_active(item);
       const int b = n_local & 1;
-      const bool next_active = pair_active(item + gridDim.x);
-      if (!active) {
+      if (!pair_active(item)) {
         // no work for this pair in the item: keep the ring / Q protocols alive (their barriers expect one arrival
-        // per MMA warp) and pre-issue S for the next item after the last stage
-        wait_q(b);
+        // per MMA warp, in phase order)
+        mbar_wait(BAR(Q_FULL + b), (uint32_t)(n_local >> 1) & 1);
         if (elect_one()) mbar_arrive(BAR(Q_EMPTY + b));
         __syncwarp();
         for (int j = 0; j < NST; ++j) {
           mbar_wait(BAR(KV_FULL + kslot), kph);
-          if (j + 1 == NST && next_active) {
-            uint32_t nslot, nph;
-            next_slot(nslot, nph);
-            wait_q(b ^ 1);
-            mbar_wait(BAR(KV_FULL + nslot), nph);
-            tc_fence_after();
-            issue_s(b ^ 1, nslot, 0, NU == 1, NU == 1);
-          }
           release_kv(false);
+          ++s_stage;
+          if (++s_slot == (uint32_t)NS) { s_slot = 0; s_ph ^= 1; }   // the S cursor is parked at this item: move it along
         }
+        s_item += gridDim.x; ++s_nl;
         continue;
       }
-      for (int u = 0; u < NU; ++u) {
-        const int half = u & 1;
-        uint32_t nslot, nph;
-        next_slot(nslot, nph);
-        const int nk = min(64, p.L - u * 64);
-        const int nch = (nk + 15) >> 4, nch0 = min(nch, 2), nch1 = nch - nch0;    // 16-key MMA steps per half
-        const uint32_t vrow16 = kv16 + kslot * stage16 + tile16 + half * 64;      // V rows of this unit (head slot 0)
-        issue_pv(0, nch0, vrow16, u == 0);
-        if (u + 1 < NU) {
-          if (half == 1) { mbar_wait(BAR(KV_FULL + nslot), nph); tc_fence_after(); }
-          issue_s(b, half == 1 ? nslot : kslot, half ^ 1, u + 2 == NU, u + 2 == NU);
-        } else if (next_active) {
-          wait_q(b ^ 1);
-          mbar_wait(BAR(KV_FULL + nslot), nph);
-          tc_fence_after();
-          issue_s(b ^ 1, nslot, 0, NU == 1, NU == 1);
+      while (lead < 3 && issue_next_s()) {}
+      int kq = 0;
+      uint32_t vrow = kv16 + kslot * stage16 + tile16;             // V rows of the current half (head slot 0)
+      for (int k = 0; k < NH; ++k) {
+        const int n_steps = k == NH - 1 ? pv_last_steps : 2;
+        const uint32_t a = bb * 32, pb = 8 * bb;
+        const bool do_s = lead <= 3 && s_prepare();                // S_{k+3} rides in the same elected block
+        mbar_wait(bg0 + P_FULL + pb, bph);
+        mbar_wait(bg1 + P_FULL + pb, bph);
+        tc_fence_after();
+        if (elect_one()) {
+          mma_ts_lohi(tc0 + 96, tc0 + a, (vrow + hs0) | lo_v, hi_v, idesc_pv, (uint32_t)k);
+          if (n_steps == 2) mma_ts_lohi(tc0 + 96, tc0 + a + 8, (vrow + hs0 + 16) | lo_v, hi_v, idesc_pv, 1u);
+          mma_commit(bg0 + PV_DONE + pb);
+          mma_ts_lohi(tc1 + 96, tc1 + a, (vrow + hs1) | lo_v, hi_v, idesc_pv, (uint32_t)k);
+          if (n_steps == 2) mma_ts_lohi(tc1 + 96, tc1 + a + 8, (vrow + hs1 + 16) | lo_v, hi_v, idesc_pv, 1u);
+          mma_commit(bg1 + PV_DONE + pb);
+          if (do_s) s_emit();
         }
-        issue_pv(1, nch1, vrow16 + 32, false);
-        ++up;
-        if (half == 1 || u + 1 == NU) release_kv(true);            // this pair is done with the K/V stage
+        __syncwarp();
+        --lead;
+        if (do_s) s_advance();
+        while (lead < 3 && issue_next_s()) {}
+        if (bb == 2) { bb = 0; bph ^= 1; } else ++bb;
+        vrow += 32;
+        if (++kq == 4 || k == NH - 1) {                            // this pair is done with the K/V stage
+          release_kv(true);
+          kq = 0;
+          vrow = kv16 + kslot * stage16 + tile16;
+        }
       }
     }
   } else {
@@ -367,9 +389,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
     const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;
     const uint32_t tcol = tmem + ((uint32_t)(quarter * 32) << 16) + g * 128;
-    const uint32_t bgrp = BAR(GRP + 8 * g);
+    const uint32_t bgrp = BAR(GRP + 16 * g);
     const int OC = HDP / 8;
-    uint32_t uc = 0;                                               // running unit counter of this group
+    uint32_t kk = 0, ph = 0;                                       // running half counter of this group, phase of its buffer
+    int bb = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int seq, h0, q0;
       decode(item, seq, h0, q0);
@@ -377,37 +400,20 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
       const bool store = group_active(g, h0, q0);
       const int head = h0 + g / QG, qt = q0 + g % QG;
       float m_ref = 0.f, l0 = 0.f, l1 = 0.f;
-      // ---- full 64-key units ----
-      const int n_full = n_last == 64 ? NU : NU - 1;
-      for (int u = 0; u < n_full; ++u, ++uc) {
-        mbar_wait(bgrp + S_FULL, uc & 1);
+      const int n_full = n_last == 32 ? NH : NH - 1;
+      int lb = 0; uint32_t lph = 0;                                // buffer / phase of the item's last half
+      for (int k = 0; k < NH; ++k, ++kk) {
+        mbar_wait(bgrp + S_FULL + 8 * bb, ph);
         tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          // P[h] is free once P.V of the previous unit's half h has completed.  Waited for in EVERY half of every
-          // unit: a parity wait is only meaningful for the phase right after the last one this thread has seen.
-          if (uc > 0) { mbar_wait(bgrp + PV_DONE + 8 * h, (uc - 1) & 1); tc_fence_after(); }
-          attn2_half<true>(tcol, bgrp, h, 32, u == 0 && h == 0, h == 1, uc, HDP, m_ref, l0, l1);
-          tc_fence_before();
-          mbar_arrive(bgrp + P_FULL + 8 * h);
-        }
-      }
-      // ---- the short last unit (n_last < 64 keys) ----
-      if (n_full < NU) {
-        mbar_wait(bgrp + S_FULL, uc & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int nkh = min(32, n_last - 32 * h);
-          if (uc > 0) { mbar_wait(bgrp + PV_DONE + 8 * h, (uc - 1) & 1); tc_fence_after(); }
-          if (nkh > 0) attn2_half<false>(tcol, bgrp, h, nkh, n_full == 0 && h == 0, h == 1 || n_last <= 32, uc, HDP, m_ref, l0, l1);
-          tc_fence_before();
-          mbar_arrive(bgrp + P_FULL + 8 * h);
-        }
-        ++uc;
+        if (k < n_full) attn2_half<true>(tcol, bgrp, bb, ph, kk, 32, k == 0, HDP, m_ref, l0, l1);
+        else attn2_half<false>(tcol, bgrp, bb, ph, kk, n_last, k == 0, HDP, m_ref, l0, l1);
+        tc_fence_before();
+        mbar_arrive(bgrp + P_FULL + 8 * bb);
+        lb = bb; lph = ph;
+        if (++bb == 3) { bb = 0; ph ^= 1; }
       }
       // ---- all keys done: O / l -> this head's slice of the o image ----
-      mbar_wait(bgrp + PV_DONE + 8, (uc - 1) & 1);
+      mbar_wait(bgrp + PV_DONE + 8 * lb, lph);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld16(tcol + 96, r);

@@ -349,7 +349,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
   __nv_bfloat16* oimg = (__nv_bfloat16*)(wsp + ws.o_img);
   float2* rope = (float2*)(wsp + ws.rope);
   const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
-  static thread_local uint32_t smem_set[4] = {0, 0, 0, 0};
+  static thread_local uint32_t smem_set[5] = {0, 0, 0, 0, 0};
   if (c.rope) {
     rope_table_kernel<<<(L * (HDP / 2) + 255) / 256, 256, 0, st>>>(rope, (const float*)(packed + p.rope), L, hd / 2, HDP / 2);
     TFL_LAUNCH_CHECK();
@@ -389,19 +389,21 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     } else {
       Attn2Params a2;
       a2.qkv = qkv; a2.o = oimg; a2.nseq = nseq; a2.heads = heads; a2.L = L; a2.NTL = NTL; a2.HDP = HDP;
-      a2.NQT = ap.NQT; a2.NU = ap.NU;
+      a2.NQT = ap.NQT;
       a2.QG = a2.NQT >= 3 ? 4 : (a2.NQT == 2 ? 2 : 1);         // 4 groups = QG query tiles x HG heads
       a2.HG = ATT2_G / a2.QG;
       a2.NQG = (a2.NQT + a2.QG - 1) / a2.QG; a2.NHG = (heads + a2.HG - 1) / a2.HG;
       a2.n_items = nseq * a2.NHG * a2.NQG;
       const uint32_t smem = attn2_smem(HDP, a2.HG, &a2.NS);
       TFL_CHECK(a2.NS >= 2, "attention K/V ring does not fit in shared memory");
-      if (smem > smem_set[3]) {
-        TFL_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[3] = smem;
+      auto kern = HDP == 16 ? attn_tc2_kernel<1> : attn_tc2_kernel<2>;
+      const int si = HDP == 16 ? 3 : 4;
+      if (smem > smem_set[si]) {
+        TFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[si] = smem;
       }
       const int grid = a2.n_items < pl->sm_count ? a2.n_items : pl->sm_count;
-      attn_tc2_kernel<<<grid, ATT2_THREADS, smem, st>>>(a2);
+      kern<<<grid, ATT2_THREADS, smem, st>>>(a2);
     }
     TFL_LAUNCH_CHECK();
     if (tail_q) {
