@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libtfl_b200.so")
+LIB_PATH = os.environ.get("TFL_LIB") or os.path.join(HERE, "csrc", "libtfl_b200.so")  # TFL_LIB: A/B builds in profiles/
 
 
 class TflConfig(C.Structure):

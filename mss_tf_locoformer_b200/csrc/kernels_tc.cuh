@@ -290,8 +290,11 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
           trace_event(tr, 8, it * NC + cc);
           if (cc == 0) _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(D2_EMPTY + t), (uint32_t)((it & 1) ^ 1));
           tc_fence_after();
+          long long wacc = 0;
           for (int s = 0; s < KS; ++s) {
+            const long long tw = tr ? clock64() : 0;
             mbar_wait(BAR(W_FULL + wslot), wph);
+            if (tr) wacc += clock64() - tw;
             tc_fence_after();
             const uint32_t wb = w16 + wslot * stage16;
             _Pragma("unroll") for (int t = 0; t < NT; ++t) {
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
           }
           __syncwarp();
           trace_event(tr, 9, it * NC + cc);
+          if (tr != nullptr && it * NC + cc < 64) tr[12 * 64 + it * NC + cc] = (unsigned long long)wacc;
         };
         for (int c = 0; c < NC; ++c) {
           trace_event(tr, 0, it * NC + c);
@@ -324,9 +328,13 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
           }
           tc_fence_after();
           trace_event(tr, 1, it * NC + c);
+          long long wacc1 = 0;
           for (int k = 0; k < KT; ++k)
             for (int hf = 0; hf < KH; ++hf) {
+              const long long tw = tr ? clock64() : 0;
               mbar_wait(BAR(W_FULL + wslot), wph);
+              if (tr) wacc1 += clock64() - tw;
+              if (tr != nullptr && it * NC + c == 14) { tr[13 * 64 + 2 * (k * KH + hf)] = (unsigned long long)tw; tr[13 * 64 + 2 * (k * KH + hf) + 1] = (unsigned long long)clock64(); }
               tc_fence_after();
               const uint32_t wb = w16 + wslot * stage16;
               _Pragma("unroll") for (int t = 0; t < NT; ++t) {
@@ -336,8 +344,10 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
                   mma_run((int)KK1, dcol, ab | lo_a, wb | lo_b1, hi, idesc1, (uint32_t)(k | hf), 2u * AR, 256u);
                 __syncwarp();
               }
+              if (tr != nullptr && it * NC + c == 14) tr[14 * 64 + 2 * (k * KH + hf)] = (unsigned long long)clock64();
               if (elect_one()) mma_commit(BAR(W_EMPTY + wslot));
               __syncwarp();
+              if (tr != nullptr && it * NC + c == 14) tr[14 * 64 + 2 * (k * KH + hf) + 1] = (unsigned long long)clock64();
               if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
             }
           if (elect_one()) {
@@ -347,6 +357,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
           }
           __syncwarp();
           trace_event(tr, 2, it * NC + c);
+          if (tr != nullptr && it * NC + c < 64) tr[11 * 64 + it * NC + c] = (unsigned long long)wacc1;
           if (c > 0) mma2(c - 1, qpar ^ 1);
           qpar ^= 1;
         }

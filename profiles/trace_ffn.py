@@ -24,6 +24,11 @@ names = {0: "m1_start", 1: "m1_ready", 2: "m1_issued", 3: "epi_d1full", 4: "epi_
          6: "epi_gfull", 7: "m2_start", 8: "m2_gfull", 9: "m2_issued"}
 base = int(t[0, 6])
 print("chunk " + " ".join(f"{names[e]:>13s}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)))
+print("(last two columns: clocks the MMA warp spent waiting for weight stages in M1 / M2 of the chunk)")
 for c in range(6, 30):
-    print(f"{c:5d} " + " ".join(f"{int(t[e, c]) - base:13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)))
+    print(f"{c:5d} " + " ".join(f"{int(t[e, c]) - base:13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)) + f" {int(t[11, c]):8d} {int(t[12, c]):8d}")
 
+print("chunk 14, per W1 stage: wait start, wait end, MMAs issued, commit issued (relative to the first)")
+b14 = int(t[13, 0])
+for st in range(8):
+    print(st, int(t[13, 2 * st]) - b14, int(t[13, 2 * st + 1]) - b14, int(t[14, 2 * st]) - b14, int(t[14, 2 * st + 1]) - b14)
