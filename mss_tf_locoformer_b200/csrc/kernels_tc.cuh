@@ -63,7 +63,7 @@ inline bool ffn_tc_geometry(int C, int H, int KT, int G, FfnTcGeom* g) {
   g->NS = (int)((TC_SMEM_MAX - off) / g->stage_bytes);
   if (g->NS > 8) g->NS = 8;
   g->smem_bytes = off + g->NS * g->stage_bytes;
-  g->threads = 32 * (6 + 4 * g->NT);
+  g->threads = 32 * (6 + 5 * g->NT);   // loader, NT + 1 MMA warps, 4 producers, 4 * NT epilogue warps
   return true;
 }
 
@@ -73,10 +73,10 @@ inline size_t tc_ffn_image_bytes(int C, int H, int K) {
   return (size_t)g.NC * (K * g.KH + g.KS) * g.stage_bytes;
 }
 
-// Weight image in consumption order.  Per hidden chunk c: the KT*KH conv1d stages W1(c, k, half)
-// (B operand [128 rows = 64 value | 64 gate] x [C/KH input channels], chunk-major) and then -- one
-// chunk late, matching the MMA issue order -- the KS transposed-conv stages W2(c - 1, s)
-// (TPS taps x [C rows] x [64 hidden channels]).
+// Weight image: first, per hidden chunk c, the KT*KH conv1d stages W1(c, k, half) (B operand [128 rows = 64 value |
+// 64 gate] x [C/KH input channels], chunk-major); then, per chunk, the KS transposed-conv stages W2(c, s)
+// (TPS taps x [C rows] x [64 hidden channels]).  The loader streams W1(q) followed by W2(q - 1) for the running
+// chunk index q, across tile-pair boundaries.
 __global__ void tc_pack_ffn_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
                                    __nv_bfloat16* __restrict__ img, int C, int H, int KT, int KH, int TPS, int KS) {
   const int NC = H / TC_HC, n1 = KT * KH, n_per = n1 + KS;
@@ -88,13 +88,9 @@ __global__ void tc_pack_ffn_kernel(const float* __restrict__ w1, const float* __
     const int g = (int)(idx / stage_elems);
     const int e = (int)(idx % stage_elems);
     int is_w1, c, sub;
-    if (g < n1) { is_w1 = 1; c = 0; sub = g; }
-    else {
-      const int gp = g - n1, blk = gp / n_per, rem = gp % n_per;
-      if (blk < NC - 1) {
-        if (rem < n1) { is_w1 = 1; c = blk + 1; sub = rem; } else { is_w1 = 0; c = blk; sub = rem - n1; }
-      } else { is_w1 = 0; c = NC - 1; sub = rem; }
-    }
+    if (g < NC * n1) { is_w1 = 1; c = g / n1; sub = g - c * n1; }
+    else { is_w1 = 0; c = (g - NC * n1) / KS; sub = (g - NC * n1) - c * KS; }
+    (void)n_per;
     float v = 0.f;
     if (is_w1) {
       const int k = sub / KH, hf = sub % KH;
@@ -200,7 +196,7 @@ __device__ __forceinline__ void mma_run(int n, uint32_t d_tmem, uint32_t a_lo, u
 }
 
 template <int NT>
-__global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom g) {
+__global__ void __launch_bounds__(192 + 160 * NT, 1) ffn_tc_kernel(FfnTcParams p, FfnTcGeom g) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,7 +212,7 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   // barrier map: 0..7 w_full, 8..15 w_empty, 16..19 a_full, 20..23 a_empty, 24..25 d1_full[tile], 26..27 d1_empty,
   // 28..29 g_full, 30..31 g_empty, 32..33 d2_full, 34..35 d2_empty; slot 48: TMEM base address
   const int W_FULL = 0, W_EMPTY = 8, A_FULL = 16, A_EMPTY = 20, D1_FULL = 24, D1_EMPTY = 26, G_FULL = 28, G_EMPTY = 30,
-            D2_FULL = 32, D2_EMPTY = 34;
+            D2_FULL = 32, D2_EMPTY = 34, F_DONE = 36;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bar + 8 * 48);
 
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) tab_b1[i] = p.b1[i];
@@ -226,12 +222,12 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
     for (uint32_t i = threadIdx.x; i < NT * g.g_buf_bytes / 4; i += blockDim.x) gz[i] = 0u;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 2 * NT); }
     for (int i = 0; i < 4; ++i) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(A_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(D1_FULL + i), 1); mbar_init(BAR(D1_EMPTY + i), 128);
       mbar_init(BAR(G_FULL + i), 128); mbar_init(BAR(G_EMPTY + i), 1);
-      mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 128);
+      mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 128); mbar_init(BAR(F_DONE + i), 128);
     }
     fence_barrier_init();
   }
@@ -244,29 +240,48 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
   unsigned long long* const tr = (blockIdx.x == 0 && lane == 0) ? g_trace : nullptr;   // diagnostic event trace
   const int n_pairs = (p.n_tiles + NT - 1) / NT;
   const int n_iter = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int stages_per_iter = NC * (KT * KH + KS);
   const uint32_t d2_col0 = 2u * 2 * TC_HC;  // after the two D1 tiles
 
   if (warp == 0) {
     // ===================== weight loader (whole warp runs the loop, one elected lane issues) =====================
+    // stage order = MMA issue order: for the running chunk index q (continuous across the CTA's tile pairs, so the
+    // first conv1d chunk of the next pair is issued BEFORE the last transposed-conv chunk of this one and the tensor
+    // pipe never drains at a pair boundary): W1(q mod NC), then W2((q - 1) mod NC); W2(NC - 1) closes the stream.
     {
       uint32_t slot = 0, ph = 0;
-      for (int it = 0; it < n_iter; ++it) {
-        const char* src = p.img;
-        for (int s = 0; s < stages_per_iter; ++s, src += g.stage_bytes) {
-          mbar_wait(BAR(W_EMPTY + slot), ph ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(BAR(W_FULL + slot), g.stage_bytes);
-            bulk_g2s(sbase + g.off_w + slot * g.stage_bytes, src, g.stage_bytes, BAR(W_FULL + slot));
+      const int n1 = KT * KH;
+      const char* const w2base = p.img + (size_t)NC * n1 * g.stage_bytes;
+      const int Q = n_iter * NC;
+      _Pragma("unroll 1") for (int q = 0; q <= Q; ++q) {
+        _Pragma("unroll 1") for (int part = 0; part < 2; ++part) {
+          const char* src; int n;
+          if (part == 0) { if (q == Q) continue; src = p.img + (size_t)(q % NC) * n1 * g.stage_bytes; n = n1; }
+          else { if (q == 0) continue; src = w2base + (size_t)((q - 1) % NC) * KS * g.stage_bytes; n = KS; }
+          _Pragma("unroll 1") for (int s = 0; s < n; ++s, src += g.stage_bytes) {
+            mbar_wait(BAR(W_EMPTY + slot), ph ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(BAR(W_FULL + slot), g.stage_bytes);
+              bulk_g2s(sbase + g.off_w + slot * g.stage_bytes, src, g.stage_bytes, BAR(W_FULL + slot));
+            }
+            __syncwarp();
+            if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp runs the control flow; elected lane issues) =====================
-    {
+  } else if (warp <= NT + 1) {
+    // ===================== MMA issuers: one warp per tile slot for the conv1d MMAs (M1), one for the transposed conv (M2) ====
+    // Issuing a tcgen05.mma costs the issuing thread 80-150 clocks in this kernel (descriptor words travel through R2UR,
+    // mbarrier polls and commits sit in between; profiles/mma_rate_bench.cu), more than the 64 clocks an
+    // M128 x N128 x K16 MMA occupies the tensor pipe -- one issuing warp left the pipe idle half of the time.  Each
+    // tile's accumulators, A / G tiles and barriers are private to the tile, and M1 / M2 of a tile use disjoint
+    // barrier sets, so the issue work is spread over NT + 1 warps (16 warps in all: four per scheduler, which keeps
+    // 128 registers per thread); they share only the weight ring, whose stages are consumed in image order.
+    // ONE elected lane runs each warp's whole persistent loop (elect.sync once, at the top: ptxas then knows a single
+    // thread is active and emits bare UTCHMMA / UTCBAR).
+    if (elect_one()) {
+      const bool is_m1 = warp <= NT;
+      const int t = is_m1 ? warp - 1 : 0;
       const uint32_t idesc1 = instr_desc(128, 2 * TC_HC), idesc2 = instr_desc(128, C);
       // descriptor words: lo = (addr >> 4) | (LBO/16 << 16); hi = SBO/16 | version(1) << 14
       const uint32_t hi = (128u >> 4) | (1u << 14);
@@ -275,137 +290,140 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
       const uint32_t lo_b2 = (uint32_t)C << 16;            // W2 stage: C rows   -> LBO = C*16
       const uint32_t KK1 = C / KH / 16;                    // MMAs per W1 stage per tile
       const uint32_t w16 = (sbase + g.off_w) >> 4, stage16 = g.stage_bytes >> 4;
-      const uint32_t g16 = (sbase + g.off_g) >> 4, gbuf16 = g.g_buf_bytes >> 4;
+      const uint32_t gb = ((sbase + g.off_g) >> 4) + t * (g.g_buf_bytes >> 4);
       const uint32_t a16 = (sbase + g.off_a) >> 4, aslot16 = g.a_slot_bytes >> 4;
       const uint32_t tap16 = (uint32_t)(TC_HC / 8) * C;    // one W2 tap = 8 chunks * C rows * 16 B
-      uint32_t wslot = 0, wph = 0;
-      uint32_t aslot[NT], aph[NT];
-#pragma unroll
-      _Pragma("unroll") for (int t = 0; t < NT; ++t) { aslot[t] = t; aph[t] = 0; }
-      uint32_t qpar = 0;                                   // parity of the running chunk counter
-      for (int it = 0; it < n_iter; ++it) {
-        auto mma2 = [&](int cc, uint32_t par) {
-          trace_event(tr, 7, it * NC + cc);
-          _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(G_FULL + t), par);
-          trace_event(tr, 8, it * NC + cc);
-          if (cc == 0) _Pragma("unroll") for (int t = 0; t < NT; ++t) mbar_wait(BAR(D2_EMPTY + t), (uint32_t)((it & 1) ^ 1));
-          tc_fence_after();
-          long long wacc = 0;
-          for (int s = 0; s < KS; ++s) {
-            const long long tw = tr ? clock64() : 0;
-            mbar_wait(BAR(W_FULL + wslot), wph);
-            if (tr) wacc += clock64() - tw;
-            tc_fence_after();
-            const uint32_t wb = w16 + wslot * stage16;
-            _Pragma("unroll") for (int t = 0; t < NT; ++t) {
-              const uint32_t gb = g16 + t * gbuf16;
-              const uint32_t dcol = tmem + d2_col0 + t * C;
-              for (int tl = 0; tl < TPS; ++tl) {
-                const int tap = s * TPS + tl;
-                if (tap >= KT) break;
-                if (elect_one())
-                  mma_run(TC_HC / 16, dcol, (gb + tap) | lo_a, (wb + tl * tap16) | lo_b2, hi, idesc2, (uint32_t)(cc | tap),
-                          2u * AR, 2u * C);
-                __syncwarp();
-              }
-            }
-            if (elect_one()) mma_commit(BAR(W_EMPTY + wslot));
-            __syncwarp();
-            if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
-          }
-          if (elect_one()) {
-            _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(G_EMPTY + t));
-          }
-          __syncwarp();
-          trace_event(tr, 9, it * NC + cc);
-          if (tr != nullptr && it * NC + cc < 64) tr[12 * 64 + it * NC + cc] = (unsigned long long)wacc;
-        };
-        for (int c = 0; c < NC; ++c) {
-          trace_event(tr, 0, it * NC + c);
-          _Pragma("unroll") for (int t = 0; t < NT; ++t) {
-            if (c == 0) mbar_wait(BAR(A_FULL + aslot[t]), aph[t]);
+      const uint32_t d1col = tmem + t * (2 * TC_HC), d2col = tmem + d2_col0 + t * C;
+      unsigned long long* const mtr = (t == 0 && blockIdx.x == 0) ? g_trace : nullptr;   // the elected lanes trace
+      uint32_t wslot = 0, wph = 0;                         // ring position of the NEXT stage in image order
+      // Every stage is released by ALL MMA warps (W_EMPTY counts 2 * NT: NT arrivals from the warps of each kind): a
+      // warp steps over a stage of the other kind by observing its full phase and arriving at once.  The ring then
+      // moves in lock step with every warp, so a parity wait always refers to the phase right after the last one the
+      // thread has seen (a warp that merely skipped slots could be lapped by the loader, or poll a slot two uses behind).
+      auto skip = [&](int n) {
+        for (int i = 0; i < n; ++i) {
+          mbar_wait(BAR(W_FULL + wslot), wph);
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(BAR(W_EMPTY + wslot)), "r"(is_m1 ? 1 : NT) : "memory");
+          if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
+        }
+      };
+      const int n1 = KT * KH;
+      if (is_m1) {
+        uint32_t aslot = t, aph = 0;
+        uint32_t qpar = 0;                                 // parity of the running chunk counter
+        for (int it = 0; it < n_iter; ++it) {
+          for (int c = 0; c < NC; ++c) {
+            trace_event(mtr, 0, it * NC + c);
+            if (c == 0) mbar_wait(BAR(A_FULL + aslot), aph);
             mbar_wait(BAR(D1_EMPTY + t), qpar ^ 1);
+            tc_fence_after();
+            trace_event(mtr, 1, it * NC + c);
+            const uint32_t ab0 = a16 + aslot * aslot16;
+            long long wacc1 = 0;
+            for (int k = 0; k < KT; ++k)
+              for (int hf = 0; hf < KH; ++hf) {
+                const long long tw = mtr ? clock64() : 0;
+                mbar_wait(BAR(W_FULL + wslot), wph);
+                if (mtr) wacc1 += clock64() - tw;
+                tc_fence_after();
+                const uint32_t wb = w16 + wslot * stage16;
+                mma_run((int)KK1, d1col, (ab0 + k + hf * KK1 * 2 * AR) | lo_a, wb | lo_b1, hi, idesc1, (uint32_t)(k | hf), 2u * AR,
+                        256u);
+                mma_commit(BAR(W_EMPTY + wslot));
+                if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
+              }
+            mma_commit(BAR(D1_FULL + t));
+            if (c == NC - 1) mma_commit(BAR(A_EMPTY + aslot));
+            trace_event(mtr, 2, it * NC + c);
+            if (mtr != nullptr && it * NC + c < 64) mtr[11 * 64 + it * NC + c] = (unsigned long long)wacc1;
+            if (it + c > 0) skip(KS);                      // the M2 stages of the previous chunk (running index)
+            qpar ^= 1;
           }
-          tc_fence_after();
-          trace_event(tr, 1, it * NC + c);
-          long long wacc1 = 0;
-          for (int k = 0; k < KT; ++k)
-            for (int hf = 0; hf < KH; ++hf) {
-              const long long tw = tr ? clock64() : 0;
+          for (int a = 0; a < NT; ++a)   // advance this tile's A slot by NT positions in the NA ring
+            if (++aslot == (uint32_t)NA) { aslot = 0; aph ^= 1; }
+        }
+        if (n_iter > 0) skip(KS);                          // the M2 stages of the very last chunk
+      } else {
+        uint32_t qpar = 0;
+        const int Q = n_iter * NC;
+        int cc = NC - 1, it2 = -1;                         // chunk / tile pair of the transposed conv issued at step q
+        for (int q = 0; q <= Q; ++q) {
+          if (q < Q) skip(n1);                             // the M1 stages of chunk q
+          if (q > 0) {
+            trace_event(mtr, 7, it2 * NC + cc);
+            _Pragma("unroll") for (int u = 0; u < NT; ++u) mbar_wait(BAR(G_FULL + u), qpar);
+            trace_event(mtr, 8, it2 * NC + cc);
+            if (cc == 0) _Pragma("unroll") for (int u = 0; u < NT; ++u) mbar_wait(BAR(D2_EMPTY + u), (uint32_t)((it2 & 1) ^ 1));
+            tc_fence_after();
+            long long wacc = 0;
+            for (int s = 0; s < KS; ++s) {
+              const long long tw = mtr ? clock64() : 0;
               mbar_wait(BAR(W_FULL + wslot), wph);
-              if (tr) wacc1 += clock64() - tw;
-              if (tr != nullptr && it * NC + c == 14) { tr[13 * 64 + 2 * (k * KH + hf)] = (unsigned long long)tw; tr[13 * 64 + 2 * (k * KH + hf) + 1] = (unsigned long long)clock64(); }
+              if (mtr) wacc += clock64() - tw;
               tc_fence_after();
               const uint32_t wb = w16 + wslot * stage16;
-              _Pragma("unroll") for (int t = 0; t < NT; ++t) {
-                const uint32_t ab = a16 + aslot[t] * aslot16 + k + hf * KK1 * 2 * AR;
-                const uint32_t dcol = tmem + t * (2 * TC_HC);
-                if (elect_one())
-                  mma_run((int)KK1, dcol, ab | lo_a, wb | lo_b1, hi, idesc1, (uint32_t)(k | hf), 2u * AR, 256u);
-                __syncwarp();
+              _Pragma("unroll") for (int u = 0; u < NT; ++u) {
+                for (int tl = 0; tl < TPS; ++tl) {
+                  const int tap = s * TPS + tl;
+                  if (tap >= KT) break;
+                  mma_run(TC_HC / 16, d2col + u * C, (gb + u * (g.g_buf_bytes >> 4) + tap) | lo_a, (wb + tl * tap16) | lo_b2, hi,
+                          idesc2, (uint32_t)(cc | tap), 2u * AR, 2u * C);
+                }
+                mma_commit(BAR(W_EMPTY + wslot));          // one arrival per tile
               }
-              if (tr != nullptr && it * NC + c == 14) tr[14 * 64 + 2 * (k * KH + hf)] = (unsigned long long)clock64();
-              if (elect_one()) mma_commit(BAR(W_EMPTY + wslot));
-              __syncwarp();
-              if (tr != nullptr && it * NC + c == 14) tr[14 * 64 + 2 * (k * KH + hf) + 1] = (unsigned long long)clock64();
               if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; }
             }
-          if (elect_one()) {
-            _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(D1_FULL + t));
-            if (c == NC - 1)
-              _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(A_EMPTY + aslot[t]));
+            _Pragma("unroll") for (int u = 0; u < NT; ++u) mma_commit(BAR(G_EMPTY + u));
+            if (cc == NC - 1) _Pragma("unroll") for (int u = 0; u < NT; ++u) mma_commit(BAR(D2_FULL + u));
+            trace_event(mtr, 9, it2 * NC + cc);
+            if (mtr != nullptr && it2 * NC + cc < 64) mtr[12 * 64 + it2 * NC + cc] = (unsigned long long)wacc;
+            qpar ^= 1;
           }
-          __syncwarp();
-          trace_event(tr, 2, it * NC + c);
-          if (tr != nullptr && it * NC + c < 64) tr[11 * 64 + it * NC + c] = (unsigned long long)wacc1;
-          if (c > 0) mma2(c - 1, qpar ^ 1);
-          qpar ^= 1;
-        }
-        mma2(NC - 1, qpar ^ 1);
-        if (elect_one()) {
-          _Pragma("unroll") for (int t = 0; t < NT; ++t) mma_commit(BAR(D2_FULL + t));
-        }
-        __syncwarp();
-        _Pragma("unroll") for (int t = 0; t < NT; ++t) {
-          for (int a = 0; a < NT; ++a)   // advance this tile's A slot by NT positions in the NA ring
-            if (++aslot[t] == (uint32_t)NA) { aslot[t] = 0; aph[t] ^= 1; }
+          if (++cc == NC) { cc = 0; ++it2; }               // step q + 1 issues the transposed conv of chunk q
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 6 + NT) {
     // ===================== A producers / output writers =====================
     // x -> RMSGroupNorm -> bf16 chunk-major A tile for the NEXT tile pair, then the final epilogue of the current
     // pair (transposed-conv accumulator + bias + residual -> y), so the SwiGLU warps never leave the chunk loop.
-    const int tp = threadIdx.x - 64;  // 0..127
+    const int tp = threadIdx.x - 32 * (2 + NT);  // 0..127
     const int G = g.G, D = C / G;
     const float rs = rsqrtf((float)D);
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;       // tile row in the final epilogue
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t slot = 0, ph = 0;
+    // (code size matters: 16 warps run five different programs, and every unrolled copy of these bodies competes
+    //  for the instruction cache -- ncu showed 'no instruction' as a top stall reason of the epilogue warps)
+    constexpr int AHEAD = NA / NT;
     auto produce = [&](int it) {
-      _Pragma("unroll") for (int t = 0; t < NT; ++t) {
+      _Pragma("unroll 1") for (int t = 0; t < NT; ++t) {
         mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
+        if (it >= AHEAD) mbar_wait(BAR(F_DONE + t), (uint32_t)(((it - AHEAD) & 1)));
+        if (warp == NT + 2 && tr != nullptr && it < 8) tr[13 * 64 + 32 + 4 * it + 2 * t] = (unsigned long long)clock64();
         uint8_t* at = smem + g.off_a + (size_t)slot * g.a_slot_bytes;
         const long long tile = ((long long)blockIdx.x + (long long)it * gridDim.x) * NT + t;
         const long long r0 = tile * TS;
-        for (int item = tp; item < AR * G; item += 128) {
-          const int row = item / G, grp = item - row * G;
-          const long long r = r0 + row;
-          bool valid = r < p.R;
-          const float* src = nullptr;
-          if (valid) {
-            const int s = (int)(r / p.P), j = (int)(r - (long long)s * p.P);
-            valid = j >= KT - 1;
-            if (valid) src = p.x + p.map.base(s) + (long long)(j - (KT - 1)) * p.map.pos_stride + grp * D;
-          }
-          if (D <= 32) {
-            // the whole group (<= 32 channels) is fetched with back-to-back independent 128-bit loads and stays in
-            // registers between the sum of squares and the scaling: one memory latency per item, x read once
-            float4 v[8];
+        const int s0 = (int)(r0 / p.P), j0 = (int)(r0 - (long long)s0 * p.P);   // one 64-bit division per tile
+        auto locate = [&](int item, int& row, int& grp) -> const float* {        // source of a (row, group) item or nullptr
+          row = item / G; grp = item - row * G;
+          if (item >= AR * G || r0 + row >= p.R) return nullptr;
+          int sq = s0, j = j0 + row;
+          while (j >= p.P) { j -= p.P; ++sq; }
+          if (j < KT - 1) return nullptr;                                          // zero rows between two sequences
+          return p.x + p.map.base(sq) + (long long)(j - (KT - 1)) * p.map.pos_stride + grp * D;
+        };
+        if (D <= 32) {
+          // A (row, group) item is <= 32 channels: fetched with back-to-back independent 128-bit loads, kept in
+          // registers between the sum of squares and the scaling (x read once).  The loads of the NEXT item are in
+          // flight while this one is normalised and stored: two memory latencies overlap instead of one per pass.
+          auto fetch = [&](const float* src, float4 (&v)[8]) {
 #pragma unroll
             for (int d = 0; d < 8; ++d)
-              v[d] = (valid && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[d] = (src != nullptr && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          auto emit = [&](const float4 (&v)[8], int row, int grp) {
             float ss = 0.f;
 #pragma unroll
             for (int d = 0; d < 8; ++d) ss += v[d].x * v[d].x + v[d].y * v[d].y + v[d].z * v[d].z + v[d].w * v[d].w;
@@ -421,7 +439,22 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
                 *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * AR + row) * 16 + (c0 & 7) * 2) = pk;
               }
             }
-          } else {
+          };
+          float4 va[8], vb[8];
+          int rowa, grpa, rowb, grpb;
+          fetch(locate(tp, rowa, grpa), va);
+          _Pragma("unroll 1") for (int item = tp; item < AR * G; item += 128) {
+            fetch(locate(item + 128, rowb, grpb), vb);
+            emit(va, rowa, grpa);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) va[d] = vb[d];
+            rowa = rowb; grpa = grpb;
+          }
+        } else {
+          for (int item = tp; item < AR * G; item += 128) {
+            int row, grp;
+            const float* src = locate(item, row, grp);
+            const bool valid = src != nullptr;
             float ss = 0.f;
             if (valid)
               for (int d = 0; d < D; d += 4) {
@@ -442,82 +475,127 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
             }
           }
         }
+        if (warp == NT + 2 && tr != nullptr && it < 8) tr[13 * 64 + 32 + 4 * it + 2 * t + 1] = (unsigned long long)clock64();
         fence_proxy_async();
         mbar_arrive(BAR(A_FULL + slot));
         if (++slot == (uint32_t)NA) { slot = 0; ph ^= 1; }
       }
     };
-    produce(0);
-    for (int it = 0; it < n_iter; ++it) {
-      if (it + 1 < n_iter) produce(it + 1);
-      _Pragma("unroll") for (int t = 0; t < NT; ++t) {
-      // ---- final: transposed-conv accumulator + bias + residual -> y ----
-      mbar_wait(BAR(D2_FULL + t), (uint32_t)(it & 1));
-      tc_fence_after();
-      const long long tile = ((long long)blockIdx.x + (long long)it * gridDim.x) * NT + t;
-      const long long ro = tile * TS + m;
-      float* dst = nullptr;
-      const float* res = nullptr;
-      if (m < TS && ro < p.R) {
-        const int s = (int)(ro / p.P), i = (int)(ro - (long long)s * p.P);
-        if (i < p.S) {
-          const long long off = p.map.base(s) + (long long)i * p.map.pos_stride;
-          dst = p.y + off; res = p.x + off;
-        }
-      }
-      int c0 = 0;
-      for (; c0 + 32 <= C; c0 += 32) {      // 32 columns per step: TMEM load and the residual loads fly together
-        uint32_t r[32];
-        tmem_ld32(lane_addr + d2_col0 + t * C + c0, r);
-        float4 xv[8];
-        if (dst != nullptr) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) xv[e] = __ldg(reinterpret_cast<const float4*>(res + c0 + 4 * e));
-        }
-        tc_wait_ld();
-        if (dst != nullptr) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 b = *reinterpret_cast<const float4*>(tab_b2 + c0 + 4 * e);
-            xv[e].x += __uint_as_float(r[4 * e]) + b.x;
-            xv[e].y += __uint_as_float(r[4 * e + 1]) + b.y;
-            xv[e].z += __uint_as_float(r[4 * e + 2]) + b.z;
-            xv[e].w += __uint_as_float(r[4 * e + 3]) + b.w;
-            *reinterpret_cast<float4*>(dst + c0 + 4 * e) = xv[e];
-          }
-        }
-      }
-      for (; c0 < C; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(lane_addr + d2_col0 + t * C + c0, r);
-        tc_wait_ld();
-        if (dst != nullptr) {
-#pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            float4 xv = __ldg(reinterpret_cast<const float4*>(res + c0 + e));
-            xv.x += __uint_as_float(r[e]) + tab_b2[c0 + e];
-            xv.y += __uint_as_float(r[e + 1]) + tab_b2[c0 + e + 1];
-            xv.z += __uint_as_float(r[e + 2]) + tab_b2[c0 + e + 2];
-            xv.w += __uint_as_float(r[e + 3]) + tab_b2[c0 + e + 3];
-            *reinterpret_cast<float4*>(dst + c0 + e) = xv;
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(BAR(D2_EMPTY + t));
-      }
-    }
+    // The A tiles run AHEAD pairs ahead.  The final epilogue of pair `it` comes FIRST in every round: the transposed
+    // conv of the next pair's first chunk waits for it (D2_EMPTY), about one chunk period after D2_FULL.
+    // The A tiles run AHEAD pairs ahead; a slot is rewritten once the MMAs that read it are done (A_EMPTY) and the
+    // epilogue group of that tile slot has finished its output pass, which borrows the slot as a staging strip (F_DONE).
+    _Pragma("unroll 1") for (int it = 0; it < n_iter; ++it) produce(it);
   } else {
     // ===================== epilogue groups (one per tile slot) =====================
-    const int t = (warp - 6) >> 2;
+    const int t = (warp - (6 + NT)) >> 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;       // tile row
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     uint8_t* gt = smem + g.off_g + (size_t)t * g.g_buf_bytes;
     uint32_t qpar = 0;
-    for (int it = 0; it < n_iter; ++it) {
-      for (int c = 0; c < NC; ++c) {
-        unsigned long long* const etr = warp == 6 ? tr : nullptr;
+    // ---- output pass of one finished tile: transposed-conv accumulator + bias + residual -> y ----
+    // TMEM hands every thread one ROW of the tile; a warp instruction that touches 32 rows of x costs 32 L1 tag cycles.
+    // So each warp passes its 32 rows through a padded strip in shared memory (the tile's own A slot: every MMA that
+    // read it completed before D2_FULL; the producers wait for F_DONE before they rewrite it), 32 columns per step, and
+    // walks the strip with 8 lanes per row (128 contiguous bytes): 4 lines per load / store instead of 32.  The
+    // residual of the next step is requested before this step's stores.
+    constexpr uint32_t FPITCH = 32 * 4 + 16;               // strip row: 32 fp32 + 16 B (conflict-free both ways)
+    const int frow = lane >> 3, fcol = (lane & 7) * 4;      // coalesced phase: row within a group of 4, first column
+    unsigned long long* const etr = warp == 6 + NT ? tr : nullptr;
+    auto finish = [&](int it) {
+      const long long tile = ((long long)blockIdx.x + (long long)it * gridDim.x) * NT + t;
+      if ((C & 31) == 0 && g.a_slot_bytes >= 128 * FPITCH) {   // the strips of the four warps must fit in the A slot
+        const int steps = C / 32;
+        int pos[8];                                        // stream position (x / y offset = pos * C) of row quarter*32 + 4*i + frow
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {
+          const int mm = quarter * 32 + 4 * i + frow;
+          const long long ro = tile * TS + mm;
+          pos[i] = -1;
+          if (mm < TS && ro < p.R) {
+            const int sq = (int)(ro / p.P), j = (int)(ro - (long long)sq * p.P);
+            if (j < p.S) pos[i] = (int)((p.map.base(sq) + (long long)j * p.map.pos_stride) / C);
+          }
+        }
+        auto fetch = [&](float4 (&xv)[8], int st) {
+          _Pragma("unroll") for (int i = 0; i < 8; ++i)
+            xv[i] = pos[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)pos[i] * C + st * 32 + fcol))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        uint8_t* strip = smem + g.off_a + (size_t)(((uint32_t)(it * NT + t)) % NA) * g.a_slot_bytes + (size_t)(quarter * 32) * FPITCH;
+        float4 xa[8], xb[8];
+        fetch(xa, 0);                                        // in flight while this warp waits for the accumulator
+        mbar_wait(BAR(D2_FULL + t), (uint32_t)(it & 1));
+        tc_fence_after();
+        trace_event(etr, 13, it);
+        _Pragma("unroll 1") for (int st = 0; st < steps; ++st) {
+          {
+            uint32_t r[32];
+            tmem_ld32(lane_addr + d2_col0 + t * C + st * 32, r);
+            tc_wait_ld();
+            _Pragma("unroll") for (int e = 0; e < 8; ++e)
+              *reinterpret_cast<uint4*>(strip + (size_t)lane * FPITCH + e * 16) = make_uint4(r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
+          }
+          if (st == steps - 1) {                             // D2 of this tile fully read
+            tc_fence_before();
+            mbar_arrive(BAR(D2_EMPTY + t));
+          }
+          __syncwarp();
+          if (st + 1 < steps) fetch(xb, st + 1);
+          const float4 b = *reinterpret_cast<const float4*>(tab_b2 + st * 32 + fcol);
+          _Pragma("unroll") for (int i = 0; i < 8; ++i) {
+            const float4 d = *reinterpret_cast<const float4*>(strip + (size_t)(4 * i + frow) * FPITCH + fcol * 4);
+            if (pos[i] >= 0) {
+              float4 o = xa[i];
+              o.x += d.x + b.x; o.y += d.y + b.y; o.z += d.z + b.z; o.w += d.w + b.w;
+              *reinterpret_cast<float4*>(p.y + (long long)pos[i] * C + st * 32 + fcol) = o;
+            }
+          }
+          __syncwarp();
+          _Pragma("unroll") for (int i = 0; i < 8; ++i) xa[i] = xb[i];
+        }
+      } else {
+        mbar_wait(BAR(D2_FULL + t), (uint32_t)(it & 1));
+        tc_fence_after();
+        const long long ro = tile * TS + m;
+        float* dst = nullptr;
+        const float* res = nullptr;
+        if (m < TS && ro < p.R) {
+          const int sq = (int)(ro / p.P), i = (int)(ro - (long long)sq * p.P);
+          if (i < p.S) {
+            const long long off = p.map.base(sq) + (long long)i * p.map.pos_stride;
+            dst = p.y + off; res = p.x + off;
+          }
+        }
+        _Pragma("unroll 1") for (int c0 = 0; c0 < C; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + d2_col0 + t * C + c0, r);
+          tc_wait_ld();
+          if (dst != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              float4 xv = __ldg(reinterpret_cast<const float4*>(res + c0 + e));
+              xv.x += __uint_as_float(r[e]) + tab_b2[c0 + e];
+              xv.y += __uint_as_float(r[e + 1]) + tab_b2[c0 + e + 1];
+              xv.z += __uint_as_float(r[e + 2]) + tab_b2[c0 + e + 2];
+              xv.w += __uint_as_float(r[e + 3]) + tab_b2[c0 + e + 3];
+              *reinterpret_cast<float4*>(dst + c0 + e) = xv;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(D2_EMPTY + t));
+      }
+      trace_event(etr, 14, it);
+      mbar_arrive(BAR(F_DONE + t));                          // the strip (this tile's A slot) may be rewritten
+    };
+    // Running chunk index q across the CTA's tile pairs.  The output pass of pair it - 1 runs right after the SwiGLU of
+    // chunk 0 of pair it: the MMA warps already have D1 of that chunk back and the hidden tile of chunk 0, so the
+    // tensor pipe keeps working on the next pair while this group writes the previous one out.
+    const int Q = n_iter * NC;
+    int c = 0, it = 0;
+    _Pragma("unroll 1") for (int q = 0; q <= Q; ++q) {
+      if (q < Q) {
         mbar_wait(BAR(D1_FULL + t), qpar);
         tc_fence_after();
         trace_event(etr, 3, it * NC + c);
@@ -559,6 +637,8 @@ __global__ void __launch_bounds__(192 + 128 * NT, 1) ffn_tc_kernel(FfnTcParams p
         trace_event(etr, 6, it * NC + c);
         qpar ^= 1;
       }
+      if (q > 0 && c == 0) finish(it - 1);
+      if (++c == NC) { c = 0; ++it; }
     }
   }
   tc_fence_before();

@@ -28,7 +28,9 @@ print("(last two columns: clocks the MMA warp spent waiting for weight stages in
 for c in range(6, 30):
     print(f"{c:5d} " + " ".join(f"{int(t[e, c]) - base:13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)) + f" {int(t[11, c]):8d} {int(t[12, c]):8d}")
 
-print("chunk 14, per W1 stage: wait start, wait end, MMAs issued, commit issued (relative to the first)")
-b14 = int(t[13, 0])
-for st in range(8):
-    print(st, int(t[13, 2 * st]) - b14, int(t[13, 2 * st + 1]) - b14, int(t[14, 2 * st]) - b14, int(t[14, 2 * st + 1]) - b14)
+print("epilogue group 0: output pass start (D2 full seen), end")
+for it in range(1, 6):
+    print(it, int(t[13, it]) - base, int(t[14, it]) - base)
+print("produce(it): A_EMPTY seen tile 0, tile 0 written, A_EMPTY seen tile 1, tile 1 written")
+for it in range(2, 8):
+    print(it, *[int(t[13, 32 + 4 * it + k]) - base for k in range(4)])
