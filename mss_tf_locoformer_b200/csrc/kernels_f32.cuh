@@ -469,12 +469,16 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
 }
 
 // --------------------------------------------------------------------------------------
-// K6 decoder: ConvTranspose2d(C, 2S, 3x3, pad 1) as a 9-tap gather (:182); one warp per
-// position, lanes over channels (conflict-free float4 weight reads), shuffle reduction;
-// writes est[b][src][t][f][re/im].  wd layout: [9 taps][8 outputs][C] (tap = dt*3+df
-// multiplies x[t+1-dt, f+1-df]).
+// K6 decoder: ConvTranspose2d(C, 2S, 3x3, pad 1) as a 9-tap gather (:182).  One warp per group of
+// DEC_P consecutive bins of one frame, lanes over channels: every weight vector read from shared
+// memory (conflict-free float4) feeds DEC_P positions (the kernel was bound by those reads at one
+// position per warp) and the three frequency taps share the DEC_P + 2 input columns.  The
+// DEC_P * 8 partial sums per lane are reduced by a transposing butterfly (31 shuffles; lane l ends
+// with the total of value l = position * 8 + output).  Writes est[b][src][t][f][re/im].
+// wd layout: [9 taps][8 outputs][C] (tap = dt*3+df multiplies x[t+1-dt, f+1-df]).
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dec_conv_kernel(const float* __restrict__ x, int n_frames, int n_freq, int C,
+constexpr int DEC_P = 4;
+__global__ void __launch_bounds__(256, 2) dec_conv_kernel(const float* __restrict__ x, int n_frames, int n_freq, int C,
                                                        int n_out, const float* __restrict__ wd,
                                                        const float* __restrict__ bias, float* __restrict__ est,
                                                        long long n_pos) {
@@ -483,44 +487,62 @@ __global__ void __launch_bounds__(256) dec_conv_kernel(const float* __restrict__
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n_src = n_out >> 1;
-  for (long long pos = (long long)blockIdx.x * wpb + warp; pos < n_pos; pos += (long long)gridDim.x * wpb) {
-    const int f = (int)(pos % n_freq);
-    const long long bt = pos / n_freq;
+  const int NG = (n_freq + DEC_P - 1) / DEC_P;                 // groups per frame
+  const long long n_groups = (n_pos / n_freq) * NG;
+  for (long long grp = (long long)blockIdx.x * wpb + warp; grp < n_groups; grp += (long long)gridDim.x * wpb) {
+    const long long bt = grp / NG;
+    const int f0 = (int)(grp - bt * NG) * DEC_P;
     const int t = (int)(bt % n_frames), b = (int)(bt / n_frames);
-    float acc[8];
+    float acc[DEC_P * 8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int k = 0; k < DEC_P * 8; ++k) acc[k] = 0.f;
+    for (int c = lane << 2; c < C; c += 128) {
 #pragma unroll
-    for (int dt = 0; dt < 3; ++dt) {
-      const int tt = t + 1 - dt;
-      if (tt < 0 || tt >= n_frames) continue;
+      for (int dt = 0; dt < 3; ++dt) {
+        const int tt = t + 1 - dt;
+        if (tt < 0 || tt >= n_frames) continue;
+        const float* px = x + (((size_t)b * n_frames + tt) * n_freq) * C + c;
+        float4 xv[DEC_P + 2];                                  // columns f0 - 1 .. f0 + DEC_P
 #pragma unroll
-      for (int df = 0; df < 3; ++df) {
-        const int ff = f + 1 - df;
-        if (ff < 0 || ff >= n_freq) continue;
-        const float* px = x + (((size_t)b * n_frames + tt) * n_freq + ff) * C;
-        const float* pw = wsm + (dt * 3 + df) * 8 * C;
-        for (int c = lane << 2; c < C; c += 128) {
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(px + c));
+        for (int j = 0; j < DEC_P + 2; ++j) {
+          const int ff = f0 - 1 + j;
+          xv[j] = (ff >= 0 && ff < n_freq) ? __ldg(reinterpret_cast<const float4*>(px + (size_t)ff * C))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int df = 0; df < 3; ++df) {
+          const float* pw = wsm + (dt * 3 + df) * 8 * C + c;
 #pragma unroll
           for (int o = 0; o < 8; ++o) {
-            const float4 w = *reinterpret_cast<const float4*>(pw + o * C + c);
-            acc[o] = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, fmaf(xv.w, w.w, acc[o]))));
+            const float4 w = *reinterpret_cast<const float4*>(pw + o * C);
+#pragma unroll
+            for (int pi = 0; pi < DEC_P; ++pi) {               // position f0 + pi reads column f0 + pi + 1 - df
+              const float4 v = xv[pi + 2 - df];
+              acc[pi * 8 + o] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[pi * 8 + o]))));
+            }
           }
         }
       }
     }
+    // transposing butterfly: after the step with offset s, a lane keeps the half of its values whose index bit
+    // log2(s) equals its own lane bit
 #pragma unroll
-    for (int o = 0; o < 8; ++o)
+    for (int s = 16, n = DEC_P * 8; s >= 1; s >>= 1, n >>= 1) {
+      const bool up = (lane & s) != 0;
 #pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sh);
-    if (lane < n_out) {
-      float val = 0.f;
-#pragma unroll
-      for (int o = 0; o < 8; ++o) if (o == lane) val = acc[o];
-      val += __ldg(&bias[lane]);
-      const int src = lane >> 1, ri = lane & 1;
-      est[(((((size_t)b * n_src + src) * n_frames + t) * n_freq + f) << 1) + ri] = val;
+      for (int i = 0; i < 16; ++i) {
+        if (i < (n >> 1)) {
+          const float keep = up ? acc[i + (n >> 1)] : acc[i];
+          const float send = up ? acc[i] : acc[i + (n >> 1)];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+    }
+    static_assert(DEC_P * 8 == 32, "one reduced value per lane");
+    const int pi = lane >> 3, o = lane & 7, f = f0 + pi;
+    if (f < n_freq && o < n_out) {
+      const int src = o >> 1, ri = o & 1;
+      est[(((((size_t)b * n_src + src) * n_frames + t) * n_freq + f) << 1) + ri] = acc[0] + __ldg(&bias[o]);
     }
   }
 }

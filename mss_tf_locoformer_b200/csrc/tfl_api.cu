@@ -578,8 +578,8 @@ int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, 
   }
   const long long n_pos = (long long)B * Tf * F;
   const char* base = (const char*)packed;
-  long long blocks = (n_pos + 7) / 8;
-  if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
+  long long blocks = ((long long)B * Tf * ((F + DEC_P - 1) / DEC_P) + 7) / 8;   // one warp per group of DEC_P bins
+  if (blocks > (long long)pl->sm_count * 2) blocks = (long long)pl->sm_count * 2;   // two resident blocks per SM, grid-stride
   dec_conv_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, Tf, F, C, pl->cfg.n_src * 2,
                                                                    (const float*)(base + pl->lay.dec_w),
                                                                    (const float*)(base + pl->lay.dec_b), est, n_pos);

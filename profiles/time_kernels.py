@@ -36,3 +36,6 @@ def timeit(fn, n=10):
 for axis in (0, 1):
     print(f"axis {axis}: ffn {timeit(lambda: eng.ffn_(0, axis, 0, x, 1)):.3f} ms   attention sub-block "
           f"{timeit(lambda: eng.attn_(0, axis, x, 1)):.3f} ms")
+
+spec = torch.randn(B, Tf, F, 2, device="cuda")
+print(f"decoder conv {timeit(lambda: eng.dec_conv(x)):.3f} ms   encoder conv + gLN {timeit(lambda: eng.enc_conv_gln(spec)):.3f} ms")
