@@ -436,7 +436,7 @@ inline uint32_t attn_tc_smem(int HDP) {
 struct QkvTcParams {
   const float* x; SeqMap map; const float* gamma; float eps;
   const char* wimg;                 // [3 parts][C/8 chunks][NPART rows][8] bf16
-  const float2* rope;               // [L][HDP/2] (cos, sin) or nullptr ("nope")
+  const float2* rope;               // [HDP/2][L] (cos, sin), frequency-major, or nullptr ("nope")
   __nv_bfloat16* qkv;               // tile images
   int C, G, L, NTL, nseq, heads, hd, HDP, NPART;
   int n_tiles;
@@ -449,7 +449,7 @@ __global__ void rope_table_kernel(float2* __restrict__ tab, const float* __restr
   const int j = i / half_pad, f = i - j * half_pad;
   float sn = 0.f, cs = 1.f;
   if (f < half) sincosf((float)j * freqs[f], &sn, &cs);   // same fp32 product as the reference's einsum
-  tab[i] = make_float2(cs, sn);
+  tab[(size_t)f * L + j] = make_float2(cs, sn);           // frequency-major: the 32 rows of a warp read contiguously
 }
 
 __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* __restrict__ wo,
@@ -548,7 +548,50 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = tile / NTL, jt = tile - s * NTL;
       const long long base = p.map.base(s);
-      if (D <= 32) {
+      if (D == 32) {
+        // Four lanes per (row, group) item, 32 contiguous bytes each: a warp instruction reads 8 rows x 128 B (8 L1
+        // tag lookups instead of 32 -- ncu had l1tex throughput at 96 % with one lane per item) and writes one
+        // 16-byte chunk per lane, 8 consecutive rows per chunk column: conflict-free.  The group's sum of squares is
+        // two shuffles.  Eight items per thread and tile, four in flight at a time.
+        const int r8 = lane >> 2, q4 = lane & 3;
+        const int pw = warp - 2;                              // producer warp 0 .. QKV_PRODUCER_WARPS - 1
+        const int n_blk = 16 * G;                             // (8-row block, group) units per tile
+#pragma unroll 1
+        for (int u0 = pw; u0 < n_blk; u0 += 4 * QKV_PRODUCER_WARPS) {
+          float4 v[4][2];
+          int rowi[4], grpi[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int unit = u0 + u * QKV_PRODUCER_WARPS;
+            const int rb = unit / G;
+            grpi[u] = unit - rb * G;
+            rowi[u] = rb * 8 + r8;
+            const int j = jt * 128 + rowi[u];
+            const bool valid = unit < n_blk && j < p.L;
+            const float* src = p.x + base + (long long)j * p.map.pos_stride + grpi[u] * 32 + q4 * 8;
+            v[u][0] = valid ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u][1] = valid ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (u0 + u * QKV_PRODUCER_WARPS >= n_blk) continue;   // warp-uniform
+            float ss = v[u][0].x * v[u][0].x + v[u][0].y * v[u][0].y + v[u][0].z * v[u][0].z + v[u][0].w * v[u][0].w +
+                       v[u][1].x * v[u][1].x + v[u][1].y * v[u][1].y + v[u][1].z * v[u][1].z + v[u][1].w * v[u][1].w;
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+            const int c0 = grpi[u] * 32 + q4 * 8;
+            const float4 g0 = *reinterpret_cast<const float4*>(tab_gamma + c0);
+            const float4 g1 = *reinterpret_cast<const float4*>(tab_gamma + c0 + 4);
+            uint4 pk;
+            pk.x = pack_bf16(v[u][0].x * inv * g0.x, v[u][0].y * inv * g0.y);
+            pk.y = pack_bf16(v[u][0].z * inv * g0.z, v[u][0].w * inv * g0.w);
+            pk.z = pack_bf16(v[u][1].x * inv * g1.x, v[u][1].y * inv * g1.y);
+            pk.w = pack_bf16(v[u][1].z * inv * g1.z, v[u][1].w * inv * g1.w);
+            *reinterpret_cast<uint4*>(at + ((size_t)(c0 >> 3) * 128 + rowi[u]) * 16) = pk;
+          }
+        }
+      } else if (D <= 32) {
         // two (row, group) items per thread and pass: 16 independent 128-bit loads in flight, x read exactly once
         for (int item0 = tp; item0 < 128 * G; item0 += 2 * NPROD) {
           float4 v[2][8];
@@ -633,7 +676,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       float2 cs[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)j * halfp + i]) : make_float2(1.f, 0.f);
+        cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)i * p.L + j]) : make_float2(1.f, 0.f);
       for (int part = 0; part < 3; ++part) {
         mbar_wait(BAR(D_FULL + part), (uint32_t)(it & 1));
         tc_fence_after();
