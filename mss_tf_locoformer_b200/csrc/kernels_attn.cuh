@@ -677,10 +677,15 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)i * p.L + j]) : make_float2(1.f, 0.f);
+      // Rows at or beyond ceil64(L) are never read by the attention kernels (attn_tc_kernel masks whole 64-key units,
+      // attn_tc2_kernel ends on a ceil16 block, the tail-row kernel reads single query rows): neither loaded from TMEM
+      // nor written -- on the time axis (259 rows in three 128-row tiles) that is 17 % of the image.
+      const int row_lim = ((p.L + 63) & ~63) - jt * 128;         // rows of this tile anyone reads
+      const bool warp_live = quarter * 32 < row_lim;
       for (int part = 0; part < 3; ++part) {
         mbar_wait(BAR(D_FULL + part), (uint32_t)(it & 1));
         tc_fence_after();
-        for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+        for (int c0 = col_lo; warp_live && c0 < col_hi; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(lane_addr + part * NPART + c0, r);
           tc_wait_ld();
@@ -699,8 +704,10 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
           }
           __nv_bfloat16* dst = p.qkv + ((((size_t)part * p.nseq + s) * p.heads + head) * NTL + jt) * tile_elems +
                                ((size_t)(d0 >> 3) * 128 + m) * 8;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(dst + 1024) = make_uint4(w[4], w[5], w[6], w[7]);
+          if (m < row_lim) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + 1024) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         }
         tc_fence_before();
         mbar_arrive(BAR(D_EMPTY + part));
