@@ -132,8 +132,10 @@ int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan,
                        tfl_stream_t stream);
 
 /* Diagnostic: process-wide switches used for A/B measurements (not part of the reference-facing surface).
- *   TFL_OPT_ATTN_KERNEL  1 = attn_tc_kernel (P through shared memory), 2 = attn_tc2_kernel (P in TMEM; default) */
-enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_COUNT = 4 };
+ *   TFL_OPT_ATTN_KERNEL  1 = attn_tc_kernel (P through shared memory), 2 = attn_tc2_kernel (P in TMEM; default)
+ *   TFL_OPT_FFN_KERNEL   1 = ffn_tc_kernel (two tiles per CTA), 2 = ffn_tc2_kernel (cta_group::2, one tile per CTA of a
+ *                        2-CTA cluster; default where the shape allows it) */
+enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_COUNT = 4 };
 int tfl_debug_set_option(int key, int value);
 
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN

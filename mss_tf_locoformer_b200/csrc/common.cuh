@@ -74,6 +74,8 @@ struct FfnPack {
   size_t w2;         // fp32 [K][H][C], tap order reversed (tap k' multiplies g[i + k'])
   size_t b2;         // [C]
   size_t tc;         // bf16 tcgen05 image (0 = none)
+  size_t tc2;        // bf16 image for the 2-CTA kernel (halves per CTA); valid when tc2_ok
+  int tc2_ok;
   int hidden;
 };
 struct PathPack {

@@ -768,6 +768,9 @@ inline size_t tc_workspace_bytes(const tfl_plan* pl, int B, int Tf, int F) {
   return (size_t)B * Tf * F * pl->cfg.emb_dim * sizeof(float);  // second residual buffer (ping-pong)
 }
 
+int tfl_option(int key);
+inline int tc_ffn2_dispatch(const tfl_plan* pl, const FfnTcParams& p, int C, int H, int K, int G, cudaStream_t st);
+
 // y = x + ConvSwiGLU(RMSGroupNorm(x)); x and y must be distinct buffers.
 inline int tc_ffn(const tfl_plan* pl, const char* packed, int layer, int axis, int j, const float* x, float* y, int B,
                   int Tf, int F, cudaStream_t st) {
@@ -789,6 +792,10 @@ inline int tc_ffn(const tfl_plan* pl, const char* packed, int layer, int axis, i
   p.b1 = (const float*)(packed + f.b1raw); p.b2 = (const float*)(packed + f.b2);
   p.img = packed + f.tc;
   p.eps = c.eps;
+  if (f.tc2_ok && tfl_option(1 /* TFL_OPT_FFN_KERNEL */) == 2) {
+    p.img = packed + f.tc2;
+    return tc_ffn2_dispatch(pl, p, c.emb_dim, f.hidden, c.conv_kernel, c.num_groups, st);
+  }
   static thread_local uint32_t smem_set[2] = {0, 0};
   if (g.smem_bytes > smem_set[g.NT - 1]) {
     if (g.NT == 2) TFL_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));

@@ -1,0 +1,626 @@
+// K4 (v2)  ffn_tc2_kernel: y = x + ConvSwiGLU(RMSGroupNorm(x)) with the MMAs issued for a PAIR of CTAs
+// (tcgen05.mma.cta_group::2, M = 256: 128 stream rows per CTA of a 2-CTA cluster).  Same math, stream tiling, A / G
+// tile layouts and epilogues as ffn_tc_kernel (kernels_tc.cuh); what changes is the resource budget that bounded it:
+//   * ONE tile per CTA, so TMEM holds a DOUBLE-buffered conv1d accumulator (D1[2] + D2[2] = 512 columns): the taps of
+//     chunk q + 1 are multiplied while SwiGLU group (q & 1) reads chunk q back -- in ffn_tc_kernel the tensor pipe
+//     idled ~2.5 k clk per chunk for that read, and both of its tiles hit the gap together; the transposed-conv
+//     accumulator D2 is double-buffered over tiles, so the output pass of a tile never holds up the next one;
+//   * the B operand (weights) is split across the pair: every CTA streams HALF of each weight stage (8 KB), so the
+//     same shared memory holds a ring twice as deep in MMA time and L2 -> SM weight traffic per tile is unchanged
+//     although the tile count per weight pass halves;
+//   * the two SwiGLU groups alternate chunks; the group that takes chunk 0 of the next tile writes the previous tile
+//     out afterwards, while the other group already works on chunk 1.
+// Roles per CTA (16 warps):  0 loader (own half of every stage)   1 conv1d MMAs   2 peer: relays "my half landed" to
+// the leader   3 transposed-conv MMAs   4-7 A-tile producers   8-11 / 12-15 SwiGLU groups of even / odd chunks.
+// Only the leader CTA (cluster rank 0) issues MMAs; tcgen05.commit ... .multicast::cluster signals both CTAs.
+// Barriers that feed the MMA warps (A_FULL, D1_EMPTY, G_FULL, D2_EMPTY, PW_FULL) live in the leader and collect one
+// arrival per warp of BOTH CTAs (remote arrive through mapa).  Verified stand-alone: profiles/cta2_selftest.cu.
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace tfl {
+
+struct Ffn2Geom {
+  int C, H, KT, G, NS;
+  int AR, TS, NC, KH, TPS, KS;
+  uint32_t half_bytes;                 // bytes of one weight stage held by one CTA
+  uint32_t a_slot_bytes, g_buf_bytes;
+  uint32_t off_a, off_g, off_w, off_tab, off_bar, smem_bytes;
+};
+constexpr int FFN2_NA = 3;             // A-tile slots: the tile being multiplied and two ahead
+constexpr int FFN2_THREADS = 512;
+
+inline bool ffn2_geometry(int C, int H, int KT, int G, Ffn2Geom* g) {
+  if (C % 32 != 0 || C > 128 || H % TC_HC != 0 || (C / G) % 4 != 0 || KT < 1 || KT > 8) return false;
+  g->C = C; g->H = H; g->KT = KT; g->G = G;
+  g->AR = 128 + KT - 1; g->TS = 128 - (KT - 1);
+  g->NC = H / TC_HC;
+  // full stage = one conv1d tap over all C input channels (128 rows x C) = two transposed-conv taps: C / 16 MMAs per
+  // stage, so the per-stage barrier work of the issuing lane (two polls, a multicast commit) is paid once per 8 MMAs
+  g->KH = 1; g->TPS = 2; g->KS = (KT + 1) / 2;
+  const uint32_t w1_full = 256u * C / g->KH;                        // 128 rows x C/KH columns bf16
+  const uint32_t w2_full = (uint32_t)g->TPS * C * TC_HC * 2;
+  if (w1_full != w2_full) return false;
+  g->half_bytes = w1_full / 2;
+  g->a_slot_bytes = (uint32_t)(C / 8) * g->AR * 16;
+  g->g_buf_bytes = (uint32_t)(TC_HC / 8) * g->AR * 16;
+  if (g->a_slot_bytes < 2u * 128u * (16 * 4 + 16)) return false;    // output strips of both groups live in the A slot
+  uint32_t off = 0;
+  g->off_a = off; off += FFN2_NA * g->a_slot_bytes;
+  g->off_g = off; off += 2 * g->g_buf_bytes;
+  g->off_tab = off; off += (2 * H + 2 * C) * 4;
+  off = (off + 15) & ~15u;
+  g->off_bar = off; off += 640;
+  off = (off + 127) & ~127u;
+  g->off_w = off;
+  if (off + 4 * g->half_bytes > (uint32_t)TC_SMEM_MAX) return false;
+  g->NS = (int)((TC_SMEM_MAX - off) / g->half_bytes);
+  if (g->NS > 12) g->NS = 12;
+  g->smem_bytes = off + g->NS * g->half_bytes;
+  return true;
+}
+
+inline size_t tc_ffn2_image_bytes(int C, int H, int K) {
+  Ffn2Geom g;
+  if (!ffn2_geometry(C, H, K, 1, &g)) return 0;
+  return (size_t)g.NC * (K * g.KH + g.KS) * 2 * g.half_bytes;
+}
+
+// Image: per hidden chunk the KT*KH conv1d stages, then per chunk the KS transposed-conv stages (as in
+// tc_pack_ffn_kernel), every stage as TWO halves -- the B rows [0, N/2) for the leader CTA, [N/2, N) for its peer --
+// each in chunk-major layout with N/2 rows.
+__global__ void tc_pack_ffn2_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                                    __nv_bfloat16* __restrict__ img, int C, int H, int KT, int KH, int TPS, int KS) {
+  const int NC = H / TC_HC, n1 = KT * KH;
+  const int CK = C / KH;
+  const long long stage_elems = 128LL * CK;
+  const long long total = (long long)NC * (n1 + KS) * stage_elems;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx / stage_elems);
+    int e = (int)(idx % stage_elems);
+    const int half = e / (int)(stage_elems / 2);
+    e -= half * (int)(stage_elems / 2);
+    float v = 0.f;
+    if (g < NC * n1) {
+      const int c = g / n1, sub = g - c * n1;
+      const int k = sub / KH, hf = sub % KH;
+      const int chunk = e / (64 * 8), n = (e / 8) % 64 + 64 * half, cc = hf * CK + chunk * 8 + (e & 7);
+      const int row = n < TC_HC ? c * TC_HC + n : H + c * TC_HC + (n - TC_HC);
+      v = w1[((size_t)row * C + cc) * KT + k];
+    } else {
+      const int c = (g - NC * n1) / KS, sub = (g - NC * n1) - c * KS;
+      const int CH = C / 2;                                  // B rows (output channels) per CTA
+      const int per_tap = (TC_HC / 8) * CH * 8;
+      const int tl = e / per_tap, e2 = e % per_tap;
+      const int chunk = e2 / (CH * 8), n = (e2 / 8) % CH + CH * half, hh = chunk * 8 + (e2 & 7);
+      const int tap = TPS * sub + tl;
+      if (tl < TPS && tap < KT) v = w2[((size_t)(c * TC_HC + hh) * C + n) * KT + (KT - 1 - tap)];
+    }
+    img[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+inline int tc_pack_ffn2(const float* w1, const float* w2, char* img, int C, int H, int K, cudaStream_t st) {
+  Ffn2Geom g;
+  if (!ffn2_geometry(C, H, K, 1, &g)) return 0;
+  tc_pack_ffn2_kernel<<<592, 256, 0, st>>>(w1, w2, (__nv_bfloat16*)img, C, H, K, g.KH, g.TPS, g.KS);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+namespace tc {
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t n_clusters_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+}
+// bookkeeping arrivals that order no data of the arriving thread (ring-slot releases by a warp that merely stepped
+// over the stage, "my half landed" relays: the data was written by the async proxy and is read by the tensor core of
+// the same SM): a release at cluster scope costs ~1 k clocks per arrive, relaxed does not
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// wait on a barrier other CTAs of the cluster arrive on (acquire at cluster scope); bounded like mbar_wait
+__device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity);
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  mbar_wait_cluster_slow(bar, parity);
+}
+__device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long waited = clock64() - t0;
+    if (waited < (1LL << 21)) continue;
+    if (*(volatile unsigned int*)&g_wait_timeout[0] != 0) return;
+    if (waited > 1000000000LL) {
+      if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
+        g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
+        __threadfence();
+      }
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void mma2_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 ad, {%1, %3};\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// four back-to-back MMAs whose descriptors advance by fixed steps, in one asm block (cf. mma_burst)
+__device__ __forceinline__ void mma2_burst4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                            uint32_t acc_first, uint32_t a_step, uint32_t b_step) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "add.u32 a1, %1, %6;\n\tadd.u32 a2, a1, %6;\n\tadd.u32 a3, a2, %6;\n\t"
+      "add.u32 b1, %2, %7;\n\tadd.u32 b2, b1, %7;\n\tadd.u32 b3, b2, %7;\n\t"
+      "mov.b64 ad, {%1, %3};\n\tmov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, p;\n\t"
+      "mov.b64 ad, {a1, %3};\n\tmov.b64 bd, {b1, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, 1;\n\t"
+      "mov.b64 ad, {a2, %3};\n\tmov.b64 bd, {b2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, 1;\n\t"
+      "mov.b64 ad, {a3, %3};\n\tmov.b64 bd, {b3, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, 1;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(b_step)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_run(int n, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                         uint32_t acc_first, uint32_t a_step, uint32_t b_step) {
+  while (n >= 4) { mma2_burst4(d_tmem, a_lo, b_lo, hi, idesc, acc_first, a_step, b_step); a_lo += 4 * a_step; b_lo += 4 * b_step; acc_first = 1; n -= 4; }
+  for (int i = 0; i < n; ++i) {
+    mma2_lohi(d_tmem, a_lo, b_lo, hi, idesc, i == 0 ? acc_first : 1u);
+    a_lo += a_step; b_lo += b_step;
+  }
+}
+// all tcgen05.mma issued so far by this thread done -> arrive on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void mma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+}  // namespace tc
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn_tc2_kernel(FfnTcParams p, Ffn2Geom g) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = g.C, H = g.H, KT = g.KT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS, NS = g.NS;
+  const int KH = g.KH, TPS = g.TPS;
+  constexpr int NA = FFN2_NA;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t peer = rank ^ 1u;
+  const uint32_t sbase = smem_u32(smem);
+  float* tab_b1 = reinterpret_cast<float*>(smem + g.off_tab);
+  float* tab_b2 = tab_b1 + 2 * H;
+  float* tab_gamma = tab_b2 + C;
+  const uint32_t bar0 = sbase + g.off_bar;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int W_FULL = 0, W_EMPTY = 12, PW_FULL = 24, A_FULL = 36, A_EMPTY = 39, D1_FULL = 42, D1_EMPTY = 44, G_FULL = 46,
+            G_EMPTY = 48, D2_FULL = 50, D2_EMPTY = 52, F_DONE = 54;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bar + 8 * 58);
+
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) tab_b1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { tab_b2[i] = p.b2[i]; tab_gamma[i] = p.gamma[i]; }
+  {  // hidden tiles: rows >= 128 are only ever read for discarded output rows; keep them finite
+    uint32_t* gz = reinterpret_cast<uint32_t*>(smem + g.off_g);
+    for (uint32_t i = threadIdx.x; i < 2 * g.g_buf_bytes / 4; i += blockDim.x) gz[i] = 0u;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 12; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 2); mbar_init(BAR(PW_FULL + i), 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(D1_FULL + i), 1); mbar_init(BAR(D1_EMPTY + i), 8);
+      mbar_init(BAR(G_FULL + i), 8); mbar_init(BAR(G_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 16); }
+    mbar_init(BAR(F_DONE), 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  unsigned long long* const tr = (blockIdx.x == 0 && lane == 0) ? g_trace : nullptr;   // diagnostic event trace
+  const int n_cl = (int)n_clusters_x(), cl = (int)cluster_id_x();
+  const int n_pairs = (p.n_tiles + 1) / 2;
+  const int n_iter = (n_pairs - cl + n_cl - 1) / n_cl;     // identical in both CTAs of the cluster
+  const int Q = n_iter * NC;                               // running chunk count
+  const int n1 = KT * KH;
+  const uint32_t d2_col0 = 256;
+  auto tile_of = [&](int it) { return ((long long)cl + (long long)it * n_cl) * 2 + (long long)rank; };
+
+  if (warp == 0) {
+    // ===================== weight loader: this CTA's half of every stage, in MMA issue order =====================
+    uint32_t slot = 0, ph = 0;
+    const char* const w1base = p.img + (size_t)rank * g.half_bytes;
+    const char* const w2base = w1base + (size_t)NC * n1 * 2 * g.half_bytes;
+    _Pragma("unroll 1") for (int q = 0; q <= Q; ++q) {
+      _Pragma("unroll 1") for (int part = 0; part < 2; ++part) {
+        const char* src; int n;
+        if (part == 0) { if (q == Q) continue; src = w1base + (size_t)(q % NC) * n1 * 2 * g.half_bytes; n = n1; }
+        else { if (q == 0) continue; src = w2base + (size_t)((q - 1) % NC) * KS * 2 * g.half_bytes; n = KS; }
+        _Pragma("unroll 1") for (int s = 0; s < n; ++s, src += 2 * g.half_bytes) {
+          mbar_wait(BAR(W_EMPTY + slot), ph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(BAR(W_FULL + slot), g.half_bytes);
+            bulk_g2s(sbase + g.off_w + slot * g.half_bytes, src, g.half_bytes, BAR(W_FULL + slot));
+          }
+          __syncwarp();
+          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== peer CTA: tell the leader that my half of a stage has landed =====================
+    if (rank == 1 && elect_one()) {
+      uint32_t slot = 0, ph = 0;
+      const int total = Q * n1 + Q * KS;
+      _Pragma("unroll 1") for (int s = 0; s < total; ++s) {
+        mbar_wait(BAR(W_FULL + slot), ph);
+        mbar_arrive_cluster_relaxed(BAR(PW_FULL + slot), 0);
+        if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (leader CTA only): warp 1 conv1d taps, warp 3 transposed conv =====================
+    if (rank == 0 && elect_one()) {
+      const bool is_m1 = warp == 1;
+      const uint32_t idesc1 = instr_desc(256, 2 * TC_HC), idesc2 = instr_desc(256, C);
+      const uint32_t hi = (128u >> 4) | (1u << 14);
+      const uint32_t lo_a = (uint32_t)AR << 16;            // LBO = AR*16 for A and G tiles
+      const uint32_t lo_b1 = 64u << 16;                    // W1 half stage: 64 rows  -> LBO = 1024
+      const uint32_t lo_b2 = (uint32_t)(C / 2) << 16;      // W2 half stage: C/2 rows -> LBO = C*8
+      const uint32_t KK1 = C / KH / 16;                    // MMAs per W1 stage
+      const uint32_t w16 = (sbase + g.off_w) >> 4, stage16 = g.half_bytes >> 4;
+      const uint32_t g16 = (sbase + g.off_g) >> 4, gbuf16 = g.g_buf_bytes >> 4;
+      const uint32_t a16 = (sbase + g.off_a) >> 4, aslot16 = g.a_slot_bytes >> 4;
+      const uint32_t tap16 = (uint32_t)(TC_HC / 8) * (C / 2);   // one W2 tap of a half stage, in 16-byte units
+      unsigned long long* const mtr = blockIdx.x == 0 ? g_trace : nullptr;
+      uint32_t wslot = 0, wph = 0;
+      long long acc_w = 0, acc_pw = 0;                       // diagnostic: clocks spent waiting for my / the peer's half
+      auto wait_stage = [&]() {
+        const long long t0 = mtr ? clock64() : 0;
+        mbar_wait(BAR(W_FULL + wslot), wph);
+        const long long t1 = mtr ? clock64() : 0;
+        mbar_wait(BAR(PW_FULL + wslot), wph);
+        if (mtr) { acc_w += t1 - t0; acc_pw += clock64() - t1; }
+        tc_fence_after();
+      };
+      auto next_stage = [&]() { if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; } };
+      // a stage of the other kind: observe it, release it at once (both CTAs' rings move in lock step with both warps)
+      auto skip = [&](int n) {
+        for (int i = 0; i < n; ++i) {
+          wait_stage();
+          mbar_arrive(BAR(W_EMPTY + wslot));
+          mbar_arrive_cluster_relaxed(BAR(W_EMPTY + wslot), 1);
+          next_stage();
+        }
+      };
+      if (is_m1) {
+        uint32_t aslot = 0, aph = 0;
+        int c = 0, it = 0;
+        _Pragma("unroll 1") for (int q = 0; q < Q; ++q) {
+          const uint32_t b = q & 1, use = (uint32_t)(q >> 1) & 1;
+          trace_event(mtr, 0, q);
+          if (c == 0) mbar_wait_cluster(BAR(A_FULL + aslot), aph);
+          mbar_wait_cluster(BAR(D1_EMPTY + b), use ^ 1);
+          tc_fence_after();
+          trace_event(mtr, 1, q);
+          const uint32_t ab0 = a16 + aslot * aslot16;
+          for (int k = 0; k < KT; ++k)
+            for (int hf = 0; hf < KH; ++hf) {
+              wait_stage();
+              const uint32_t wb = w16 + wslot * stage16;
+              mma2_run((int)KK1, tmem + b * 128, (ab0 + k + hf * KK1 * 2 * AR) | lo_a, wb | lo_b1, hi, idesc1, (uint32_t)(k | hf),
+                       2u * AR, 128u);
+              mma2_commit(BAR(W_EMPTY + wslot));
+              next_stage();
+            }
+          mma2_commit(BAR(D1_FULL + b));
+          if (c == NC - 1) mma2_commit(BAR(A_EMPTY + aslot));
+          trace_event(mtr, 2, q);
+          if (mtr != nullptr && q < 64) { mtr[11 * 64 + q] = (unsigned long long)acc_w; mtr[12 * 64 + q] = (unsigned long long)acc_pw; }
+          acc_w = acc_pw = 0;
+          if (q > 0) skip(KS);                               // the transposed-conv stages of chunk q - 1
+          if (++c == NC) {
+            c = 0; ++it;
+            if (++aslot == (uint32_t)NA) { aslot = 0; aph ^= 1; }
+          }
+        }
+        if (Q > 0) skip(KS);
+      } else {
+        int cc = NC - 1, it2 = -1;                           // chunk / tile of the transposed conv issued at step q
+        _Pragma("unroll 1") for (int q = 0; q <= Q; ++q) {
+          if (q < Q) skip(n1);
+          if (q > 0) {
+            const uint32_t b = (q - 1) & 1, use = (uint32_t)((q - 1) >> 1) & 1;
+            trace_event(mtr, 7, q - 1);
+            mbar_wait_cluster(BAR(G_FULL + b), use);
+            const uint32_t d2b = it2 & 1;                   // D2 is double-buffered over tiles: the output pass of tile it2 - 2
+            if (cc == 0) mbar_wait_cluster(BAR(D2_EMPTY + d2b), (uint32_t)(((it2 >> 1) & 1) ^ 1));
+            tc_fence_after();
+            trace_event(mtr, 8, q - 1);
+            const uint32_t gb = g16 + b * gbuf16;
+            for (int s = 0; s < KS; ++s) {
+              wait_stage();
+              const uint32_t wb = w16 + wslot * stage16;
+              for (int tl = 0; tl < TPS; ++tl) {
+                const int tap = s * TPS + tl;
+                if (tap >= KT) break;
+                mma2_run(TC_HC / 16, tmem + d2_col0 + d2b * C, (gb + tap) | lo_a, (wb + tl * tap16) | lo_b2, hi, idesc2, (uint32_t)(cc | tap),
+                         2u * AR, (uint32_t)C);
+              }
+              mma2_commit(BAR(W_EMPTY + wslot));
+              next_stage();
+            }
+            mma2_commit(BAR(G_EMPTY + b));
+            if (cc == NC - 1) mma2_commit(BAR(D2_FULL + d2b));
+            trace_event(mtr, 9, q - 1);
+          }
+          if (++cc == NC) { cc = 0; ++it2; }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== A producers: x -> RMSGroupNorm -> bf16 chunk-major A tile, two tiles ahead =====================
+    const int tp = threadIdx.x - 128;  // 0..127
+    const int G = g.G, D = C / G;
+    const float rs = rsqrtf((float)D);
+    uint32_t slot = 0, ph = 0;
+    _Pragma("unroll 1") for (int it = 0; it < n_iter; ++it) {
+      mbar_wait(BAR(A_EMPTY + slot), ph ^ 1);
+      if (it >= NA) mbar_wait(BAR(F_DONE), (uint32_t)((it - NA) & 1));   // the output pass of tile it - NA used this slot
+      uint8_t* at = smem + g.off_a + (size_t)slot * g.a_slot_bytes;
+      const long long r0 = tile_of(it) * TS;
+      const int s0 = (int)(r0 / p.P), j0 = (int)(r0 - (long long)s0 * p.P);
+      auto locate = [&](int item, int& row, int& grp) -> const float* {
+        row = item / G; grp = item - row * G;
+        if (item >= AR * G || r0 + row >= p.R) return nullptr;
+        int sq = s0, j = j0 + row;
+        while (j >= p.P) { j -= p.P; ++sq; }
+        if (j < KT - 1) return nullptr;
+        return p.x + p.map.base(sq) + (long long)(j - (KT - 1)) * p.map.pos_stride + grp * D;
+      };
+      auto fetch = [&](const float* src, float4 (&v)[8]) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          v[d] = (src != nullptr && 4 * d < D) ? __ldg(reinterpret_cast<const float4*>(src + 4 * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto emit = [&](const float4 (&v)[8], int row, int grp) {
+        float ss = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) ss += v[d].x * v[d].x + v[d].y * v[d].y + v[d].z * v[d].z + v[d].w * v[d].w;
+        const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          if (4 * d < D) {
+            const int c0 = grp * D + 4 * d;
+            const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
+            uint2 pk;
+            pk.x = pack_bf16(v[d].x * inv * gm.x, v[d].y * inv * gm.y);
+            pk.y = pack_bf16(v[d].z * inv * gm.z, v[d].w * inv * gm.w);
+            *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * AR + row) * 16 + (c0 & 7) * 2) = pk;
+          }
+        }
+      };
+      float4 va[8], vb[8];
+      int rowa, grpa, rowb, grpb;
+      fetch(locate(tp, rowa, grpa), va);
+      _Pragma("unroll 1") for (int item = tp; item < AR * G; item += 128) {
+        fetch(locate(item + 128, rowb, grpb), vb);
+        emit(va, rowa, grpa);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) va[d] = vb[d];
+        rowa = rowb; grpa = grpb;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {                                       // one arrival per producer warp of either CTA, in the leader
+        if (rank == 0) mbar_arrive(BAR(A_FULL + slot)); else mbar_arrive_cluster(BAR(A_FULL + slot), 0);
+      }
+      if (++slot == (uint32_t)NA) { slot = 0; ph ^= 1; }
+    }
+  } else {
+    // ===================== SwiGLU groups: group b takes the chunks with running index q = b (mod 2) =====================
+    const int b = (warp - 8) >> 2;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;       // tile row
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* gt = smem + g.off_g + (size_t)b * g.g_buf_bytes;
+    constexpr uint32_t FPITCH = 16 * 4 + 16;               // output strip row: 16 fp32 + 16 B
+    const int frow = lane >> 2, fcol = (lane & 3) * 4;      // coalesced phase: 4 lanes per row, 8 rows per instruction
+    unsigned long long* const etr = warp == 8 ? tr : nullptr;
+    auto arrive_leader = [&](int bar_index) {                // one arrival per warp, on the leader's barrier
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) mbar_arrive(BAR(bar_index)); else mbar_arrive_cluster(BAR(bar_index), 0); }
+    };
+    // Output pass of a finished tile: transposed-conv accumulator + bias + residual -> y, in steps of 16 columns.
+    // Group b owns the columns [b * C/2, (b + 1) * C/2) and spreads its C / 32 steps over its chunks of the NEXT tile
+    // (D2 is double-buffered over tiles), so the pass rides in the slack between two SwiGLU chunks instead of holding
+    // the group for a whole tile's worth of global round trips.  TMEM hands every thread one ROW; each warp passes its
+    // 32 rows through a padded strip in shared memory (the finished tile's own A slot; the producers wait for F_DONE)
+    // and walks it with 4 lanes per row (64 contiguous bytes): the read-modify-write of x / y touches 8 lines per
+    // instruction instead of 32.  The residual of the next step is requested before this step's stores.
+    const int fin_steps = C / 32;                            // steps of this group per tile
+    auto finish_steps = [&](int it, int k0, int n) {
+      const long long tile = tile_of(it);
+      const int d2b = it & 1;
+      const int col0 = b * (C / 2);
+      int pos[4];
+      _Pragma("unroll") for (int i = 0; i < 4; ++i) {
+        const int mm = quarter * 32 + 8 * i + frow;
+        const long long ro = tile * TS + mm;
+        pos[i] = -1;
+        if (mm < TS && ro < p.R) {
+          const int sq = (int)(ro / p.P), j = (int)(ro - (long long)sq * p.P);
+          if (j < p.S) pos[i] = (int)((p.map.base(sq) + (long long)j * p.map.pos_stride) / C);
+        }
+      }
+      auto fetch = [&](float4 (&xv)[4], int k) {
+        _Pragma("unroll") for (int i = 0; i < 4; ++i)
+          xv[i] = pos[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)pos[i] * C + col0 + k * 16 + fcol))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      uint8_t* strip = smem + g.off_a + (size_t)((uint32_t)it % NA) * g.a_slot_bytes + (size_t)b * (128 * FPITCH) +
+                       (size_t)(quarter * 32) * FPITCH;
+      float4 xa[4], xb[4];
+      fetch(xa, k0);
+      if (k0 == 0) {
+        mbar_wait(BAR(D2_FULL + d2b), (uint32_t)((it >> 1) & 1));
+        trace_event(etr, 13, it);
+      }
+      tc_fence_after();
+      _Pragma("unroll 1") for (int k = k0; k < k0 + n; ++k) {
+        {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + d2_col0 + d2b * C + col0 + k * 16, r);
+          tc_wait_ld();
+          _Pragma("unroll") for (int e = 0; e < 4; ++e)
+            *reinterpret_cast<uint4*>(strip + (size_t)lane * FPITCH + e * 16) = make_uint4(r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
+        }
+        if (k == fin_steps - 1) {                            // this group's half of D2 fully read
+          tc_fence_before();
+          arrive_leader(D2_EMPTY + d2b);
+        }
+        __syncwarp();
+        if (k + 1 < k0 + n) fetch(xb, k + 1);
+        const float4 bb = *reinterpret_cast<const float4*>(tab_b2 + col0 + k * 16 + fcol);
+        _Pragma("unroll") for (int i = 0; i < 4; ++i) {
+          const float4 d = *reinterpret_cast<const float4*>(strip + (size_t)(8 * i + frow) * FPITCH + fcol * 4);
+          if (pos[i] >= 0) {
+            float4 o = xa[i];
+            o.x += d.x + bb.x; o.y += d.y + bb.y; o.z += d.z + bb.z; o.w += d.w + bb.w;
+            *reinterpret_cast<float4*>(p.y + (long long)pos[i] * C + col0 + k * 16 + fcol) = o;
+          }
+        }
+        __syncwarp();
+        _Pragma("unroll") for (int i = 0; i < 4; ++i) xa[i] = xb[i];
+      }
+      if (k0 + n == fin_steps) {
+        trace_event(etr, 14, it);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(F_DONE));             // this group's strips (the tile's A slot) may be rewritten
+      }
+    };
+    int fin_it = -1, fin_k = 0;                              // tile whose output pass is in progress, steps done
+    _Pragma("unroll 1") for (int q = b; q < Q + 2; q += 2) {
+      const int c = q % NC;
+      const uint32_t use = (uint32_t)(q >> 1) & 1;
+      if (q < Q) {
+        mbar_wait(BAR(D1_FULL + b), use);
+        tc_fence_after();
+        trace_event(etr, 3, q);
+        uint32_t packed[TC_HC / 2];
+        const float* bv = tab_b1 + c * TC_HC;
+        const float* bg = tab_b1 + H + c * TC_HC;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(lane_addr + b * 128 + half * 32, rv);
+          tmem_ld32(lane_addr + b * 128 + TC_HC + half * 32, rg);
+          tc_wait_ld();
+          if (half == 1) {  // D1[b] fully read: hand it back before the math
+            tc_fence_before();
+            arrive_leader(D1_EMPTY + b);
+            trace_event(etr, 4, q);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float hv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float val = __uint_as_float(rv[i + u]) + bv[half * 32 + i + u];
+              const float gate = __uint_as_float(rg[i + u]) + bg[half * 32 + i + u];
+              hv[u] = swiglu_fast(val, gate);
+            }
+            packed[half * 16 + (i >> 1)] = pack_bf16(hv[0], hv[1]);
+          }
+        }
+        trace_event(etr, 10, q);
+        mbar_wait(BAR(G_EMPTY + b), use ^ 1);    // the transposed-conv MMAs of chunk q - 2 are done with G[b]
+        trace_event(etr, 5, q);
+#pragma unroll
+        for (int ch = 0; ch < TC_HC / 8; ++ch)
+          *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
+              make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+        fence_proxy_async();
+        arrive_leader(G_FULL + b);
+        trace_event(etr, 6, q);
+      }
+      // a slice of the output pass of the previous tile (all that is left at this group's last chunk of a tile)
+      const int prev = q / NC - 1;
+      if (prev != fin_it) { fin_it = prev; fin_k = 0; }
+      if (fin_it >= 0 && fin_it < n_iter && fin_k < fin_steps) {
+        const int left = fin_steps - fin_k;
+        const bool last_chance = q >= Q || c + 2 >= NC;
+        const int n = last_chance ? left : 2;
+        finish_steps(fin_it, fin_k, n < left ? n : left);
+        fin_k += n < left ? n : left;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// y = x + ConvSwiGLU(RMSGroupNorm(x)) with the 2-CTA kernel; `img2` is the tc_pack_ffn2 image.
+inline int tc_ffn2_launch(const tfl_plan* pl, const FfnTcParams& p0, const Ffn2Geom& g, cudaStream_t st) {
+  FfnTcParams p = p0;
+  p.n_tiles = (int)((p.R + g.TS - 1) / g.TS);
+  static thread_local uint32_t smem_set = 0;
+  if (g.smem_bytes > smem_set) {
+    TFL_CUDA(cudaFuncSetAttribute(ffn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    smem_set = g.smem_bytes;
+  }
+  const int n_pairs = (p.n_tiles + 1) / 2;
+  int clusters = pl->sm_count / 2;
+  if (n_pairs < clusters) clusters = n_pairs;
+  ffn_tc2_kernel<<<2 * clusters, FFN2_THREADS, g.smem_bytes, st>>>(p, g);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int tc_ffn2_dispatch(const tfl_plan* pl, const FfnTcParams& p, int C, int H, int K, int G, cudaStream_t st) {
+  Ffn2Geom g;
+  TFL_CHECK(ffn2_geometry(C, H, K, G, &g), "shape not covered by the 2-CTA FFN kernel");
+  return tc_ffn2_launch(pl, p, g, st);
+}
+
+}  // namespace tfl

@@ -67,8 +67,11 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
     for (int i = 0; i < 64; ++i)
       if (mbar_try_wait(bar, parity)) return;
+    const long long waited = clock64() - t0;
+    if (waited < (1LL << 21)) continue;        // keep global memory out of the polling loop (a ~1.5 k clk load per 64 polls
+                                               // sat between every producer -> consumer handoff of the pipelines)
     if (*(volatile unsigned int*)&g_wait_timeout[0] != 0) return;
-    if (clock64() - t0 > 1000000000LL) {
+    if (waited > 1000000000LL) {
       if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
         g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
         __threadfence();

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc2.cuh"
 #include "kernels_attn.cuh"
 #include "kernels_attn2.cuh"
 #include "kernels_bs.cuh"
@@ -16,7 +17,8 @@
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static int g_options[TFL_OPT_COUNT] = {2, 0, 0, 0};   // tfl_debug_set_option
+static int g_options[TFL_OPT_COUNT] = {2, 2, 0, 0};   // tfl_debug_set_option
+int tfl_option(int key) { return g_options[key]; }
 unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -84,6 +86,8 @@ static void build_layout(tfl_plan* pl) {
       f.w1 = take((size_t)K * C * 2 * f.hidden); f.b1 = take(2 * f.hidden); f.b1raw = take(2 * f.hidden);
       f.w2 = take((size_t)K * f.hidden * C); f.b2 = take(C);
       f.tc = take(tc_ffn_image_bytes(C, f.hidden, K) / sizeof(float));
+      f.tc2_ok = tc_ffn2_image_bytes(C, f.hidden, K) > 0;
+      f.tc2 = take(tc_ffn2_image_bytes(C, f.hidden, K) / sizeof(float));
     }
     p.attn_gamma = take(C);
     p.rope = take(pl->head_dim / 2 + 1);
@@ -187,6 +191,7 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
         permute(w2, dst(f.w2), 1, K, H, C, 0, -1, (long long)C * K, K, K - 1, -1, st);
         copy(b2, f.b2, C);
         TFL_CHECK(tc_pack_ffn(w1, b1, w2, b2, (char*)packed + f.tc, C, H, K, st) == 0, "tc_pack_ffn failed");
+        if (f.tc2_ok) TFL_CHECK(tc_pack_ffn2(w1, w2, (char*)packed + f.tc2, C, H, K, st) == 0, "tc_pack_ffn2 failed");
       }
       copy(w[i++], p.attn_gamma, C);
       if (c.rope) copy(w[i++], p.rope, pl->head_dim / 2);
