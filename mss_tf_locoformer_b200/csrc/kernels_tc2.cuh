@@ -10,8 +10,9 @@
 //     although the tile count per weight pass halves;
 //   * the two SwiGLU groups alternate chunks; the group that takes chunk 0 of the next tile writes the previous tile
 //     out afterwards, while the other group already works on chunk 1.
-// Roles per CTA (16 warps):  0 loader (own half of every stage)   1 conv1d MMAs   2 peer: relays "my half landed" to
-// the leader   3 transposed-conv MMAs   4-7 A-tile producers   8-11 / 12-15 SwiGLU groups of even / odd chunks.
+// Roles per CTA (16 warps):  0 / 2 loaders of the conv1d / transposed-conv weight rings (own half of every stage)
+// 1 / 3 leader: conv1d / transposed-conv MMAs, peer: relays "my half of the stage landed" to the leader
+// 4-7 A-tile producers   8-11 / 12-15 SwiGLU groups of even / odd chunks.
 // Only the leader CTA (cluster rank 0) issues MMAs; tcgen05.commit ... .multicast::cluster signals both CTAs.
 // Barriers that feed the MMA warps (A_FULL, D1_EMPTY, G_FULL, D2_EMPTY, PW_FULL) live in the leader and collect one
 // arrival per warp of BOTH CTAs (remote arrive through mapa).  Verified stand-alone: profiles/cta2_selftest.cu.
@@ -21,7 +22,7 @@
 namespace tfl {
 
 struct Ffn2Geom {
-  int C, H, KT, G, NS;
+  int C, H, KT, G, NS, NSA, NSB;     // weight ring stages: total, conv1d ring, transposed-conv ring
   int AR, TS, NC, KH, TPS, KS;
   uint32_t half_bytes;                 // bytes of one weight stage held by one CTA
   uint32_t a_slot_bytes, g_buf_bytes;
@@ -55,7 +56,11 @@ inline bool ffn2_geometry(int C, int H, int KT, int G, Ffn2Geom* g) {
   g->off_w = off;
   if (off + 4 * g->half_bytes > (uint32_t)TC_SMEM_MAX) return false;
   g->NS = (int)((TC_SMEM_MAX - off) / g->half_bytes);
-  if (g->NS > 12) g->NS = 12;
+  if (g->NS > 14) g->NS = 14;
+  g->NSB = g->NS / 3 < 2 ? 2 : g->NS / 3; if (g->NSB > 6) g->NSB = 6;
+  g->NSA = g->NS - g->NSB; if (g->NSA > 8) g->NSA = 8;
+  if (g->NSA < 2) return false;
+  g->NS = g->NSA + g->NSB;
   g->smem_bytes = off + g->NS * g->half_bytes;
   return true;
 }
@@ -224,9 +229,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
   float* tab_gamma = tab_b2 + C;
   const uint32_t bar0 = sbase + g.off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  const int W_FULL = 0, W_EMPTY = 12, PW_FULL = 24, A_FULL = 36, A_EMPTY = 39, D1_FULL = 42, D1_EMPTY = 44, G_FULL = 46,
-            G_EMPTY = 48, D2_FULL = 50, D2_EMPTY = 52, F_DONE = 54;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bar + 8 * 58);
+  // two independent weight rings (conv1d stages: A, transposed-conv stages: B), each with its own loader, relay and
+  // consumer, so neither MMA warp ever waits for -- or steps over -- the other kind's stages
+  const int WA_FULL = 0, WA_EMPTY = 8, PWA_FULL = 16, WB_FULL = 24, WB_EMPTY = 30, PWB_FULL = 36, A_FULL = 42, A_EMPTY = 45,
+            D1_FULL = 48, D1_EMPTY = 50, G_FULL = 52, G_EMPTY = 54, D2_FULL = 56, D2_EMPTY = 58, F_DONE = 60;
+  const int NSA = g.NSA, NSB = g.NSB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bar + 8 * 62);
 
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) tab_b1[i] = p.b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) { tab_b2[i] = p.b2[i]; tab_gamma[i] = p.gamma[i]; }
@@ -235,7 +243,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
     for (uint32_t i = threadIdx.x; i < 2 * g.g_buf_bytes / 4; i += blockDim.x) gz[i] = 0u;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 12; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 2); mbar_init(BAR(PW_FULL + i), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(BAR(WA_FULL + i), 1); mbar_init(BAR(WA_EMPTY + i), 1); mbar_init(BAR(PWA_FULL + i), 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(BAR(WB_FULL + i), 1); mbar_init(BAR(WB_EMPTY + i), 1); mbar_init(BAR(PWB_FULL + i), 1); }
     for (int i = 0; i < NA; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(D1_FULL + i), 1); mbar_init(BAR(D1_EMPTY + i), 8);
@@ -264,41 +273,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
   const uint32_t d2_col0 = 256;
   auto tile_of = [&](int it) { return ((long long)cl + (long long)it * n_cl) * 2 + (long long)rank; };
 
-  if (warp == 0) {
-    // ===================== weight loader: this CTA's half of every stage, in MMA issue order =====================
+  const uint32_t ringA = sbase + g.off_w, ringB = ringA + (uint32_t)NSA * g.half_bytes;
+  if (warp == 0 || warp == 2) {
+    // ===================== weight loaders: warp 0 the conv1d stages, warp 2 the transposed-conv stages (this CTA's half) ====
+    const bool isA = warp == 0;
+    const int per_chunk = isA ? n1 : KS, nslots = isA ? NSA : NSB;
+    const int FULL = isA ? WA_FULL : WB_FULL, EMPTY = isA ? WA_EMPTY : WB_EMPTY;
+    const uint32_t ring = isA ? ringA : ringB;
+    const char* const base = p.img + (size_t)rank * g.half_bytes + (isA ? 0 : (size_t)NC * n1 * 2 * g.half_bytes);
     uint32_t slot = 0, ph = 0;
-    const char* const w1base = p.img + (size_t)rank * g.half_bytes;
-    const char* const w2base = w1base + (size_t)NC * n1 * 2 * g.half_bytes;
-    _Pragma("unroll 1") for (int q = 0; q <= Q; ++q) {
-      _Pragma("unroll 1") for (int part = 0; part < 2; ++part) {
-        const char* src; int n;
-        if (part == 0) { if (q == Q) continue; src = w1base + (size_t)(q % NC) * n1 * 2 * g.half_bytes; n = n1; }
-        else { if (q == 0) continue; src = w2base + (size_t)((q - 1) % NC) * KS * 2 * g.half_bytes; n = KS; }
-        _Pragma("unroll 1") for (int s = 0; s < n; ++s, src += 2 * g.half_bytes) {
-          mbar_wait(BAR(W_EMPTY + slot), ph ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(BAR(W_FULL + slot), g.half_bytes);
-            bulk_g2s(sbase + g.off_w + slot * g.half_bytes, src, g.half_bytes, BAR(W_FULL + slot));
-          }
-          __syncwarp();
-          if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+    int c = 0;
+    _Pragma("unroll 1") for (int q = 0; q < Q; ++q) {
+      const char* src = base + (size_t)c * per_chunk * 2 * g.half_bytes;
+      _Pragma("unroll 1") for (int s = 0; s < per_chunk; ++s, src += 2 * g.half_bytes) {
+        mbar_wait(BAR(EMPTY + slot), ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(BAR(FULL + slot), g.half_bytes);
+          bulk_g2s(ring + slot * g.half_bytes, src, g.half_bytes, BAR(FULL + slot));
         }
+        __syncwarp();
+        if (++slot == (uint32_t)nslots) { slot = 0; ph ^= 1; }
       }
+      if (++c == NC) c = 0;
     }
-  } else if (warp == 2) {
-    // ===================== peer CTA: tell the leader that my half of a stage has landed =====================
-    if (rank == 1 && elect_one()) {
+  } else if (rank == 1 && (warp == 1 || warp == 3)) {
+    // ===================== peer CTA: tell the leader that my half of a stage has landed (one relay per ring) ==========
+    if (elect_one()) {
+      const bool isA = warp == 1;
+      const int total = Q * (isA ? n1 : KS), nslots = isA ? NSA : NSB;
+      const int FULL = isA ? WA_FULL : WB_FULL, PFULL = isA ? PWA_FULL : PWB_FULL;
       uint32_t slot = 0, ph = 0;
-      const int total = Q * n1 + Q * KS;
       _Pragma("unroll 1") for (int s = 0; s < total; ++s) {
-        mbar_wait(BAR(W_FULL + slot), ph);
-        mbar_arrive_cluster_relaxed(BAR(PW_FULL + slot), 0);
-        if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+        mbar_wait(BAR(FULL + slot), ph);
+        mbar_arrive_cluster_relaxed(BAR(PFULL + slot), 0);
+        if (++slot == (uint32_t)nslots) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1 || warp == 3) {
-    // ===================== MMA issuers (leader CTA only): warp 1 conv1d taps, warp 3 transposed conv =====================
-    if (rank == 0 && elect_one()) {
+    // ===================== MMA issuers (leader CTA): warp 1 conv1d taps, warp 3 transposed conv =====================
+    if (elect_one()) {
       const bool is_m1 = warp == 1;
       const uint32_t idesc1 = instr_desc(256, 2 * TC_HC), idesc2 = instr_desc(256, C);
       const uint32_t hi = (128u >> 4) | (1u << 14);
@@ -306,34 +319,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
       const uint32_t lo_b1 = 64u << 16;                    // W1 half stage: 64 rows  -> LBO = 1024
       const uint32_t lo_b2 = (uint32_t)(C / 2) << 16;      // W2 half stage: C/2 rows -> LBO = C*8
       const uint32_t KK1 = C / KH / 16;                    // MMAs per W1 stage
-      const uint32_t w16 = (sbase + g.off_w) >> 4, stage16 = g.half_bytes >> 4;
+      const uint32_t stage16 = g.half_bytes >> 4;
       const uint32_t g16 = (sbase + g.off_g) >> 4, gbuf16 = g.g_buf_bytes >> 4;
       const uint32_t a16 = (sbase + g.off_a) >> 4, aslot16 = g.a_slot_bytes >> 4;
       const uint32_t tap16 = (uint32_t)(TC_HC / 8) * (C / 2);   // one W2 tap of a half stage, in 16-byte units
       unsigned long long* const mtr = blockIdx.x == 0 ? g_trace : nullptr;
       uint32_t wslot = 0, wph = 0;
       long long acc_w = 0, acc_pw = 0;                       // diagnostic: clocks spent waiting for my / the peer's half
-      auto wait_stage = [&]() {
-        const long long t0 = mtr ? clock64() : 0;
-        mbar_wait(BAR(W_FULL + wslot), wph);
-        const long long t1 = mtr ? clock64() : 0;
-        mbar_wait(BAR(PW_FULL + wslot), wph);
-        if (mtr) { acc_w += t1 - t0; acc_pw += clock64() - t1; }
-        tc_fence_after();
-      };
-      auto next_stage = [&]() { if (++wslot == (uint32_t)NS) { wslot = 0; wph ^= 1; } };
-      // a stage of the other kind: observe it, release it at once (both CTAs' rings move in lock step with both warps)
-      auto skip = [&](int n) {
-        for (int i = 0; i < n; ++i) {
-          wait_stage();
-          mbar_arrive(BAR(W_EMPTY + wslot));
-          mbar_arrive_cluster_relaxed(BAR(W_EMPTY + wslot), 1);
-          next_stage();
-        }
-      };
       if (is_m1) {
+        const uint32_t w16 = ringA >> 4;
         uint32_t aslot = 0, aph = 0;
-        int c = 0, it = 0;
+        int c = 0;
         _Pragma("unroll 1") for (int q = 0; q < Q; ++q) {
           const uint32_t b = q & 1, use = (uint32_t)(q >> 1) & 1;
           trace_event(mtr, 0, q);
@@ -344,54 +340,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
           const uint32_t ab0 = a16 + aslot * aslot16;
           for (int k = 0; k < KT; ++k)
             for (int hf = 0; hf < KH; ++hf) {
-              wait_stage();
+              const long long t0 = mtr ? clock64() : 0;
+              mbar_wait(BAR(WA_FULL + wslot), wph);
+              const long long t1 = mtr ? clock64() : 0;
+              mbar_wait(BAR(PWA_FULL + wslot), wph);
+              if (mtr) { acc_w += t1 - t0; acc_pw += clock64() - t1; }
+              tc_fence_after();
               const uint32_t wb = w16 + wslot * stage16;
               mma2_run((int)KK1, tmem + b * 128, (ab0 + k + hf * KK1 * 2 * AR) | lo_a, wb | lo_b1, hi, idesc1, (uint32_t)(k | hf),
                        2u * AR, 128u);
-              mma2_commit(BAR(W_EMPTY + wslot));
-              next_stage();
+              mma2_commit(BAR(WA_EMPTY + wslot));
+              if (++wslot == (uint32_t)NSA) { wslot = 0; wph ^= 1; }
             }
           mma2_commit(BAR(D1_FULL + b));
           if (c == NC - 1) mma2_commit(BAR(A_EMPTY + aslot));
           trace_event(mtr, 2, q);
           if (mtr != nullptr && q < 64) { mtr[11 * 64 + q] = (unsigned long long)acc_w; mtr[12 * 64 + q] = (unsigned long long)acc_pw; }
           acc_w = acc_pw = 0;
-          if (q > 0) skip(KS);                               // the transposed-conv stages of chunk q - 1
           if (++c == NC) {
-            c = 0; ++it;
+            c = 0;
             if (++aslot == (uint32_t)NA) { aslot = 0; aph ^= 1; }
           }
         }
-        if (Q > 0) skip(KS);
       } else {
-        int cc = NC - 1, it2 = -1;                           // chunk / tile of the transposed conv issued at step q
-        _Pragma("unroll 1") for (int q = 0; q <= Q; ++q) {
-          if (q < Q) skip(n1);
-          if (q > 0) {
-            const uint32_t b = (q - 1) & 1, use = (uint32_t)((q - 1) >> 1) & 1;
-            trace_event(mtr, 7, q - 1);
-            mbar_wait_cluster(BAR(G_FULL + b), use);
-            const uint32_t d2b = it2 & 1;                   // D2 is double-buffered over tiles: the output pass of tile it2 - 2
-            if (cc == 0) mbar_wait_cluster(BAR(D2_EMPTY + d2b), (uint32_t)(((it2 >> 1) & 1) ^ 1));
+        const uint32_t w16 = ringB >> 4;
+        int cc = 0, it2 = 0;
+        _Pragma("unroll 1") for (int q = 0; q < Q; ++q) {
+          const uint32_t b = q & 1, use = (uint32_t)(q >> 1) & 1;
+          trace_event(mtr, 7, q);
+          mbar_wait_cluster(BAR(G_FULL + b), use);
+          const uint32_t d2b = it2 & 1;                     // D2 is double-buffered over tiles: the output pass of tile it2 - 2
+          if (cc == 0) mbar_wait_cluster(BAR(D2_EMPTY + d2b), (uint32_t)(((it2 >> 1) & 1) ^ 1));
+          tc_fence_after();
+          trace_event(mtr, 8, q);
+          const uint32_t gb = g16 + b * gbuf16;
+          for (int s = 0; s < KS; ++s) {
+            mbar_wait(BAR(WB_FULL + wslot), wph);
+            mbar_wait(BAR(PWB_FULL + wslot), wph);
             tc_fence_after();
-            trace_event(mtr, 8, q - 1);
-            const uint32_t gb = g16 + b * gbuf16;
-            for (int s = 0; s < KS; ++s) {
-              wait_stage();
-              const uint32_t wb = w16 + wslot * stage16;
-              for (int tl = 0; tl < TPS; ++tl) {
-                const int tap = s * TPS + tl;
-                if (tap >= KT) break;
-                mma2_run(TC_HC / 16, tmem + d2_col0 + d2b * C, (gb + tap) | lo_a, (wb + tl * tap16) | lo_b2, hi, idesc2, (uint32_t)(cc | tap),
-                         2u * AR, (uint32_t)C);
-              }
-              mma2_commit(BAR(W_EMPTY + wslot));
-              next_stage();
+            const uint32_t wb = w16 + wslot * stage16;
+            for (int tl = 0; tl < TPS; ++tl) {
+              const int tap = s * TPS + tl;
+              if (tap >= KT) break;
+              mma2_run(TC_HC / 16, tmem + d2_col0 + d2b * C, (gb + tap) | lo_a, (wb + tl * tap16) | lo_b2, hi, idesc2, (uint32_t)(cc | tap),
+                       2u * AR, (uint32_t)C);
             }
-            mma2_commit(BAR(G_EMPTY + b));
-            if (cc == NC - 1) mma2_commit(BAR(D2_FULL + d2b));
-            trace_event(mtr, 9, q - 1);
+            mma2_commit(BAR(WB_EMPTY + wslot));
+            if (++wslot == (uint32_t)NSB) { wslot = 0; wph ^= 1; }
           }
+          mma2_commit(BAR(G_EMPTY + b));
+          if (cc == NC - 1) mma2_commit(BAR(D2_FULL + d2b));
+          trace_event(mtr, 9, q);
           if (++cc == NC) { cc = 0; ++it2; }
         }
       }
