@@ -214,6 +214,32 @@ __device__ __forceinline__ void mma2_commit(uint32_t bar) {
 }
 }  // namespace tc
 
+// Two SwiGLUs at once on packed fp32 pairs (FADD2 / FMUL2 / FFMA2): (value + bv) * (gate + bg) * sigmoid(gate + bg) for
+// two adjacent hidden channels, returned as a bf16 pair.  4.5 instructions per element instead of 7.5 -- the SwiGLU
+// groups, not the tensor pipe, pace ffn_tc2_kernel.
+__device__ __forceinline__ uint32_t swiglu_pair_bf16(uint32_t v0, uint32_t v1, uint32_t g0, uint32_t g1, float2 bv, float2 bg) {
+  unsigned long long v, gt, b1, b2, hf, t;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(v0), "r"(v1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(gt) : "r"(g0), "r"(g1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b1) : "f"(bv.x), "f"(bv.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(bg.x), "f"(bg.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(hf) : "f"(0.5f));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(gt) : "l"(b2));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(gt), "l"(hf));
+  float a0, a1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(t));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+  asm("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(t) : "l"(hf));            // sigmoid = 0.5 * tanh(g / 2) + 0.5
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(gt));
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(t));
+  float h0, h1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(v));
+  return tc::pack_bf16(h0, h1);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn_tc2_kernel(FfnTcParams p, Ffn2Geom g) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -559,16 +585,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
             trace_event(etr, 4, q);
           }
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float hv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float val = __uint_as_float(rv[i + u]) + bv[half * 32 + i + u];
-              const float gate = __uint_as_float(rg[i + u]) + bg[half * 32 + i + u];
-              hv[u] = swiglu_fast(val, gate);
-            }
-            packed[half * 16 + (i >> 1)] = pack_bf16(hv[0], hv[1]);
-          }
+          for (int i = 0; i < 32; i += 2)
+            packed[half * 16 + (i >> 1)] = swiglu_pair_bf16(rv[i], rv[i + 1], rg[i], rg[i + 1],
+                                                            *reinterpret_cast<const float2*>(bv + half * 32 + i),
+                                                            *reinterpret_cast<const float2*>(bg + half * 32 + i));
         }
         trace_event(etr, 10, q);
         mbar_wait(BAR(G_EMPTY + b), use ^ 1);    // the transposed-conv MMAs of chunk q - 2 are done with G[b]
@@ -587,9 +607,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
       if (fin_it >= 0 && fin_it < n_iter && fin_k < fin_steps) {
         const int left = fin_steps - fin_k;
         const bool last_chance = q >= Q || c + 2 >= NC;
-        const int n = last_chance ? left : 2;
-        finish_steps(fin_it, fin_k, n < left ? n : left);
-        fin_k += n < left ? n : left;
+        // the single-purpose resource comes first: when this group's next accumulator is already waiting, read it back
+        // (the conv1d MMAs two chunks on need the buffer) and leave the output pass for a later gap
+        bool busy = false;
+        if (!last_chance && q + 2 < Q) {
+          int rdy = lane == 0 ? (int)mbar_try_wait(BAR(D1_FULL + b), (uint32_t)((q + 2) >> 1) & 1) : 0;
+          busy = __shfl_sync(0xffffffffu, rdy, 0) != 0;
+        }
+        if (!busy) {
+          const int n = last_chance ? left : (left < 2 ? left : 2);
+          finish_steps(fin_it, fin_k, n);
+          fin_k += n;
+        }
       }
     }
   }

@@ -188,3 +188,24 @@ def test_ffn_tc_wide_single_tile_variant(pkg):
         branch, x0 = _ffn_oracle(sd, cfg, xin, 0, axis, 0)
         got = eng.ffn_(0, axis, 0, xin.cuda().clone(), 1).cpu() - x0
         assert oracle.si_sdr_db(got, branch) > 40.0, axis
+
+
+def test_ffn_tc_kernel_variants_agree(pkg):
+    """TFL_OPT_FFN_KERNEL: the 1-CTA (two tiles per CTA) and the 2-CTA (cta_group::2) kernels compute the same FFN."""
+    from mss_tf_locoformer_b200 import _lib
+    lib = _lib.load()
+    model = _random_model(pkg, VARIANT_D).cuda().eval()
+    eng = model._ready()
+    g = torch.Generator().manual_seed(11)
+    xin = torch.randn(2, 9, 300, VARIANT_D["emb_dim"], generator=g).cuda()
+    out = {}
+    try:
+        for opt in (1, 2):
+            assert lib.tfl_debug_set_option(1, opt) == 0
+            out[opt] = [eng.ffn_(0, axis, 1, xin.clone(), 1) for axis in (0, 1)]
+    finally:
+        lib.tfl_debug_set_option(1, 2)
+    for a, b in zip(out[1], out[2]):
+        branch = (a - xin).float()
+        assert float((a - b).abs().max()) <= 2e-2 * float(branch.abs().max())   # the 2-CTA kernel's order of accumulation differs
+        assert oracle.si_sdr_db((b - xin).cpu(), branch.cpu()) > 50.0
