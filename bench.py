@@ -316,7 +316,7 @@ def main():
         achieved = k_flops / (k_ms / 1e3) / 1e12
         traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this very launch shape
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn_ncu_b8_v2.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn2_ncu_b8.json")))
             if B == 8 and args.precision == "bf16":
                 traffic = cap["traffic_bytes_per_launch"]
         except (OSError, KeyError, ValueError):

@@ -359,7 +359,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
         _Pragma("unroll 1") for (int q = 0; q < Q; ++q) {
           const uint32_t b = q & 1, use = (uint32_t)(q >> 1) & 1;
           trace_event(mtr, 0, q);
-          if (c == 0) mbar_wait_cluster(BAR(A_FULL + aslot), aph);
+          if (c == 0) {
+            const long long ta = mtr ? clock64() : 0;
+            mbar_wait_cluster(BAR(A_FULL + aslot), aph);
+            if (mtr != nullptr && q < 64) mtr[15 * 64 + q] = (unsigned long long)(clock64() - ta);   // waited for the A tiles
+          }
           mbar_wait_cluster(BAR(D1_EMPTY + b), use ^ 1);
           tc_fence_after();
           trace_event(mtr, 1, q);
