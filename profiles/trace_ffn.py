@@ -34,5 +34,3 @@ for it in range(1, 6):
 print("produce(it): A_EMPTY seen tile 0, tile 0 written, A_EMPTY seen tile 1, tile 1 written")
 for it in range(2, 8):
     print(it, *[int(t[13, 32 + 4 * it + k]) - base for k in range(4)])
-print("2-CTA kernel: clocks the conv1d warp waited for the A tiles at the first chunk of tiles 1..9:",
-      [int(t[15, 6 * k]) for k in range(1, 10)])
