@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Headline benchmark: separated audio-seconds per second of TFLocoformerMSS on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|reference-gpu]
+                    [--precision bf16|fp32] [--variant D|Y] [--batch B] [--track SECONDS] [--model mss|bs]
 
 Workload (BASELINE.json configs[1], "Variant D" of SURVEY.md F4): n_fft 2048, hop 1024, 6 layers,
 emb_dim 128, 4 heads, macaron ConvSwiGLU [384, 384], 4 sources; one step = one batch of 6-s 44.1 kHz
@@ -9,6 +10,10 @@ mono segments (stereo mixture averaged to mono, as every reference caller does) 
 forward(mixture) -> dict of sources.  Random-init weights, synthetic mixtures.  N > 1: one process
 per GPU (torchrun), each rank separates its own batch every step (segment sharding, no data-path
 collective), time = max over ranks.
+
+Multi-rank discipline: the process group is torn down right after the last timed collective; every
+rank-0-only leg (kernel micro-timing, CPU baseline) runs after that, so no peer ever sits in an NCCL
+kernel behind host work.  The CPU baseline runs at N = 1 only.
 """
 import argparse
 import json
@@ -19,6 +24,7 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import torch
 
@@ -27,12 +33,29 @@ sys.path.insert(0, ROOT)
 
 SR = 44100
 SEG = 264600  # 6 s
-VARIANT_D = dict(n_fft=2048, hop_length=1024, n_sources=4, n_layers=6, emb_dim=128, norm_type="rmsgroupnorm",
-                 num_groups=4, tf_order="ft", n_heads=4, flash_attention=True, attention_dim=128, pos_enc="rope",
-                 ffn_type=["swiglu_conv1d", "swiglu_conv1d"], ffn_hidden_dim=[384, 384], conv1d_kernel=4,
-                 conv1d_shift=1, dropout=0.0, eps=1e-5)
+MAC = ["swiglu_conv1d", "swiglu_conv1d"]
+VARIANTS = {
+    # BASELINE.json's parenthetical = class defaults (models/mss_tflocoformer.py:104-129) + macaron [384, 384]
+    "D": dict(n_fft=2048, hop_length=1024, n_sources=4, n_layers=6, emb_dim=128, norm_type="rmsgroupnorm",
+              num_groups=4, tf_order="ft", n_heads=4, flash_attention=True, attention_dim=128, pos_enc="rope",
+              ffn_type=MAC, ffn_hidden_dim=[384, 384], conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5),
+    # configs/musdb18.yaml:22-43 as committed (dropout forced to 0: inference)
+    "Y": dict(n_fft=2048, hop_length=512, n_sources=4, n_layers=4, emb_dim=96, norm_type="rmsgroupnorm",
+              num_groups=4, tf_order="ft", n_heads=4, flash_attention=True, attention_dim=96, pos_enc="rope",
+              ffn_type=MAC, ffn_hidden_dim=[384, 384], conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5),
+}
+VARIANT_D = VARIANTS["D"]
+WORKLOADS = {
+    "D": "musdb18 Variant D (n_fft 2048, hop 1024, 6 layers, emb 128, macaron 384) 6-s segments",
+    "Y": "musdb18.yaml as committed, Variant Y (n_fft 2048, hop 512, 4 layers, emb 96, macaron 384) 6-s segments",
+}
 METRIC = "separated audio-sec/sec"
-WORKLOAD = "musdb18 Variant D (n_fft 2048, hop 1024, 6 layers, emb 128, macaron 384) 6-s segments"
+WORKLOAD = WORKLOADS["D"]
+# BASELINE config 4: standalone/bslocoformer_separator.py defaults at emb 128, stereo, 4 sources, masking
+BS_CFG = dict(num_spk=4, n_layers=6, emb_dim=128, norm_type="rmsgroupnorm", num_groups=4, tf_order="ft", n_heads=4,
+              flash_attention=True, attention_dim=128, pos_enc="rope", ffn_type=MAC, ffn_hidden_dim=[384, 384],
+              conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5, sample_rate=44100, stft_size=2048,
+              masking=True, stereo=True)
 
 
 def algorithmic_flops(cfg, batch, n_samples):
@@ -120,44 +143,152 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_forward(cfg, sd, mix, threads):
+# ---- the reference's own implementation (oracle/_ref = the unmodified files, staged by oracle/build_ref.py) ----
+def reference_model(cfg, state_dict, device="cpu"):
+    """-> (model, kind).  kind "reference": the unmodified reference TFLocoformerMSS from oracle/_ref;
+    kind "port": the oracle restatement (when oracle/_ref has not been staged)."""
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    from oracle import build_ref
+    if build_ref.available():
+        cls = build_ref.load()["TFLocoformerMSS"]
+        m = cls(**cfg).eval()
+        m.load_state_dict(state_dict, strict=True)
+        return m.to(device), "reference"
     import oracle
+
+    class Port:
+        def __call__(self, mix):
+            return oracle.mss_forward(state_dict, cfg, mix)
+    return Port(), "port"
+
+
+def cpu_forward(model, mix, threads):
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
-    out = oracle.mss_forward(sd, cfg, mix)
+    with torch.no_grad():
+        out = model(mix)
     return out, time.perf_counter() - t0
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm (oracle port; the reference is PyTorch-on-CPU here and its RoPE
-    dependency is not installable) on the host cores, bounded sample per step."""
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation (models/mss_tflocoformer.py:184-258, unmodified, from
+    oracle/_ref) on all host cores; one step = one mono segment of the same workload (6 s when the run fits ~7 minutes,
+    else a shorter cut, stated in `sample`).  Rank 0 only."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cfg = dict(VARIANT_D)
+    cfg = dict(VARIANTS[args.variant])
     model = make_state_dict(cfg)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    budget = 150.0 / max(1, args.steps + args.warmup)          # seconds of CPU per step
-    est_rate = 0.2 * min(1.0, cores / 8.0)                      # x real time measured on 8 EPYC cores (BASELINE.md)
-    audio_s = min(6.0, max(0.25, budget * est_rate))
-    n = int(audio_s * SR)
+    ref, kind = reference_model(cfg, sd)
+    est_rate = (0.22 if kind == "reference" else 0.1) * min(2.0, cores / 8.0)   # x real time, BASELINE.md section 2
+    audio_s = min(6.0, max(1.0, 420.0 / max(1, args.steps) * est_rate))
+    if audio_s >= 4.5:
+        audio_s = 6.0
+    n = int(round(audio_s * SR))
     mix = make_mixture(1, n)
+    warm = make_mixture(1, SR)                 # warm-up steps only page the code in and spin the thread pool up
     for _ in range(args.warmup):
-        cpu_oracle_forward(cfg, sd, mix, cores)
+        cpu_forward(ref, warm, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_oracle_forward(cfg, sd, mix, cores)
+        cpu_forward(ref, mix, cores)
     dt = time.perf_counter() - t0
     value = args.steps * n / SR / dt
-    sample = f"{n / SR:.2f}-s mono segment, batch 1, fp32, {args.steps} steps"
+    sample = (f"{n / SR:.2f}-s mono segment, batch 1, fp32, {args.steps} steps, "
+              f"{'unmodified reference TFLocoformerMSS (oracle/_ref)' if kind == 'reference' else 'oracle port'}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS[args.variant], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def time_reference_gpu(cfg, sd, dev, batch, steps, mode):
+    """The unmodified reference model, eager, on the GPU: `mode` "bf16" = torch.autocast(bfloat16) with
+    flash_attention=True (the reference's validation setting, training/train.py:214-215), "fp32" = TF32 off and
+    flash_attention=False.  -> audio-s/s, ms per step."""
+    c = dict(cfg)
+    c["flash_attention"] = mode == "bf16"
+    ref, kind = reference_model(c, sd, dev)
+    if kind != "reference":
+        return None
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mix = make_mixture(batch, SEG).to(dev)
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16" else torch.autocast("cuda", enabled=False)
+    with torch.no_grad(), ctx:
+        for _ in range(2):
+            ref(mix)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ref(mix)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del ref
+    torch.cuda.empty_cache()
+    return {"value": batch * SEG / SR / (ms / 1e3), "unit": "audio-s/s", "ms_per_step": ms, "batch": batch, "mode": mode,
+            "what": "unmodified reference TFLocoformerMSS, PyTorch eager on this GPU (cuDNN / cuBLAS / SDPA kernels)"}
+
+
+def run_reference_gpu(args, rank):
+    """--impl reference-gpu: the vendor-library bar (SURVEY 8d last row).  Rank 0 only, one GPU."""
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    cfg = dict(VARIANTS[args.variant])
+    model = make_state_dict(cfg)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    bf = time_reference_gpu(cfg, sd, dev, args.batch, args.steps, "bf16")
+    if bf is None:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref not staged (python -m oracle.build_ref)"}))
+        return
+    fp = time_reference_gpu(cfg, sd, dev, min(args.batch, 2), max(1, args.steps // 4), "fp32")
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": METRIC, "value": bf["value"], "unit": "audio-s/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": 2, "ms_per_step": bf["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.variant], "batch_per_gpu": args.batch}, "bf16_autocast": bf, "fp32_tf32_off": fp}))
+
+
+def run_bs(args, dev):
+    """BASELINE config 4: BSLocoformerSeparator (stereo, 4 sources, masking) on spec [B, 2, 259, 1025] complex64."""
+    import mss_tf_locoformer_b200 as pkg
+    from mss_tf_locoformer_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    model = pkg.BSLocoformerSeparator(**BS_CFG).eval().to(dev)
+    model.precision = args.precision
+    B = args.batch
+    mix = make_mixture(2 * B, SEG).reshape(B, 2, SEG)
+    win = torch.hann_window(2048)
+    spec = torch.stft(mix.reshape(2 * B, SEG), 2048, 1024, window=win, return_complex=True)      # [2B, F, Tf]
+    spec = spec.transpose(1, 2).reshape(B, 2, spec.shape[2], spec.shape[1]).contiguous().to(dev)  # [B, 2, Tf, F]
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            model(spec)
+        torch.cuda.synchronize()
+        n0 = lib.tfl_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            model(spec)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({
+        "metric": METRIC, "value": B * SEG / SR / (ms / 1e3), "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "BS-Locoformer (62 bands, stereo, 4 sources, masking, 6 layers, emb 128) on 6-s stereo "
+                               "spectrograms [B, 2, 259, 1025]", "batch_per_gpu": B, "precision": args.precision},
+        "gpu_launches": int(lib.tfl_launch_count() - n0)}))
 
 
 def main():
@@ -165,10 +296,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--variant", default="D", choices=sorted(VARIANTS))
+    ap.add_argument("--model", default="mss", choices=["mss", "bs"])
     ap.add_argument("--batch", type=int, default=8, help="6-s segments per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-gpu", action="store_true",
+                    help="also time the unmodified reference model eager on this GPU and add `reference_gpu` to the line")
     ap.add_argument("--track", type=float, default=0.0,
                     help="BASELINE config 3: separate ONE synthetic track of this many seconds, 6-s segments at 50 %% overlap "
                          "sharded over the ranks (strong scaling); prints its own JSON line")
@@ -179,7 +314,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu(args, rank)
         return
 
     import torch.distributed as dist
@@ -188,10 +326,14 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.model == "bs":
+        if rank == 0:
+            run_bs(args, dev)
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    cfg = dict(VARIANT_D)
+    cfg = dict(VARIANTS[args.variant])
     model = make_state_dict(cfg).to(dev)
     model.precision = args.precision
     B = args.batch
@@ -205,6 +347,14 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def finish_group():
+        """Last collective of the run: nothing rank-local may follow while a peer still waits on NCCL."""
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
 
     def timed(fn, steps):
         sync_all()
@@ -242,6 +392,7 @@ def main():
         for _ in range(max(1, args.warmup // 3)):
             step_track()
         ms = timed(step_track, args.steps)
+        finish_group()
         if rank == 0:
             print(json.dumps({
                 "metric": METRIC, "value": args.track * args.steps / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
@@ -249,12 +400,10 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
                 "data": "synthetic",
                 "config": {"workload": f"full-track {args.track:.0f}-s mono, {len(segment_starts(n_track, SEG))} segments of 6 s at "
-                                       f"50 % overlap, sharded over {world} rank(s), NCCL sum-reduce stitch",
+                                       f"50 % overlap, sharded over {world} rank(s), halo exchange + all-gather stitch",
                            "batch_per_gpu": B, "precision": args.precision}}))
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
         return
+
     for _ in range(args.warmup):
         step_resident()
     n0 = lib.tfl_launch_count()
@@ -264,88 +413,102 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    finish_group()          # ---- no collective below this line ----
+    if rank != 0:
+        return
+
     audio_s = world * B * SEG / SR
     value = audio_s * args.steps / (ms / 1e3)
     e2e_value = audio_s * args.steps / (ms_e2e / 1e3)
-
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "segment_samples": SEG, "precision": args.precision,
+        "config": {"workload": WORKLOADS[args.variant], "batch_per_gpu": B, "segment_samples": SEG,
+                   "precision": args.precision,
                    "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
                    "x_realtime_per_gpu": value / world},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": world * mix_host.numel() * 4,
                 "d2h_bytes_per_step": world * out_host.numel() * 4},
         "gpu_launches": int(launches) * world,
+        "clocks": clocks.summary(),
     }
-    if rank == 0:
-        line["clocks"] = clocks.summary()
-        fl = algorithmic_flops(cfg, B, SEG)
-        line["config"]["tflops_total_algorithmic"] = fl["total"] * world * args.steps / (ms / 1e3) / 1e12
-        # ---- roofline of the dominant kernel: the ConvSwiGLU FFN (83 % of FLOPs), frequency axis ----
-        peaks = {}
+    fl = algorithmic_flops(cfg, B, SEG)
+    line["config"]["tflops_total_algorithmic"] = fl["total"] * world * args.steps / (ms / 1e3) / 1e12
+    # ---- roofline of the dominant kernel: the ConvSwiGLU FFN (83 % of FLOPs), frequency axis ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    # the kernel below is timed alone (10 back-to-back launches): the burst cuBLAS figure is its denominator; the
+    # whole-step fraction uses the sustained one (B200_PROFILING.md)
+    peak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.4 PF"
+    line["config"]["step_frac_of_sustained_bf16_peak"] = line["config"]["tflops_total_algorithmic"] / peak_sustained
+    eng = model._ready()
+    prec = 1 if args.precision == "bf16" else 0
+    Tf, F = 1 + SEG // cfg["hop_length"], cfg["n_fft"] // 2 + 1
+    hid_last = cfg["ffn_hidden_dim"][-1]
+    x = torch.randn(B, Tf, F, cfg["emb_dim"], device=dev)
+    y = torch.empty_like(x)
+    for _ in range(3):
+        eng.ffn_out(0, 0, 0, x, y, prec)
+    reps = 10
+    l0 = lib.tfl_launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.ffn_out(0, 0, 0, x, y, prec)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps
+    k_launches = (lib.tfl_launch_count() - l0) // reps
+    k_flops = ffn_call_flops(cfg, B, SEG, 0, hid_last)
+    achieved = k_flops / (k_ms / 1e3) / 1e12
+    traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this very launch shape
+    for cap_name in ("r02_ffn2_ncu_b8.json", "r01_ffn2_ncu_b8.json"):
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        # the kernel below is timed alone (10 back-to-back launches): the burst cuBLAS figure is its denominator; the
-        # whole-step fraction uses the sustained one (B200_PROFILING.md)
-        peak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_sustained = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.4 PF"
-        line["config"]["step_frac_of_sustained_bf16_peak"] = line["config"]["tflops_total_algorithmic"] / peak_sustained
-        eng = model._ready()
-        prec = 1 if args.precision == "bf16" else 0
-        Tf, F = 1 + SEG // cfg["hop_length"], cfg["n_fft"] // 2 + 1
-        x = torch.randn(B, Tf, F, cfg["emb_dim"], device=dev)
-        for _ in range(3):
-            eng.ffn_(0, 0, 0, x, prec)
-        reps = 10
-        l0 = lib.tfl_launch_count()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            eng.ffn_(0, 0, 0, x, prec)
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        k_launches = (lib.tfl_launch_count() - l0) // reps
-        k_flops = ffn_call_flops(cfg, B, SEG, 0, 384)
-        achieved = k_flops / (k_ms / 1e3) / 1e12
-        traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this very launch shape
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ffn2_ncu_b8.json")))
-            if B == 8 and args.precision == "bf16":
+            cap = json.load(open(os.path.join(ROOT, "profiles", cap_name)))
+            if B == 8 and args.precision == "bf16" and args.variant == "D":
                 traffic = cap["traffic_bytes_per_launch"]
+            break
         except (OSError, KeyError, ValueError):
-            pass
-        line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak, "frac_of_sustained": achieved / peak_sustained, "traffic": traffic,
-                            "kernel": "conv_swiglu_ffn (freq axis)",
-                            "launches_per_call": int(k_launches), "ms_per_call": k_ms, "peak_source": peak_src,
-                            "flops_per_call": k_flops}
-        del x
-        if not args.no_cpu_baseline:
-            # ---- CPU baseline: the oracle port on the host cores, one 1.5-s segment (~10-20 s of CPU) ----
-            cores = os.cpu_count() or 1
-            n = SEG // 4
-            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-            mix = make_mixture(1, n)
-            want, dt = cpu_oracle_forward(cfg, sd, mix, cores)
-            with torch.no_grad():
-                got = model(mix.to(dev))
-            import oracle
-            worst = min(oracle.si_sdr_db(got[k].cpu(), want[k]) for k in want)
-            err = max(float((got[k].cpu() - want[k]).abs().max()) for k in want)
-            line["cpu_baseline"] = {"value": n / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": f"one {n / SR:.2f}-s mono segment, batch 1, fp32 oracle, {dt:.1f} s"}
-            line["parity"] = {"vs": "cpu oracle, same weights and input", "worst_si_sdr_db": worst, "max_abs": err}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            continue
+    line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "frac_of_sustained": achieved / peak_sustained, "traffic": traffic,
+                        "kernel": "conv_swiglu_ffn (freq axis), out-of-place kernel launch alone",
+                        "launches_per_call": int(k_launches), "ms_per_call": k_ms, "peak_source": peak_src,
+                        "flops_per_call": k_flops}
+    del x, y
+    if world == 1 and args.reference_gpu:
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        line["reference_gpu"] = {"bf16_autocast": time_reference_gpu(cfg, sd, dev, B, 3, "bf16"),
+                                 "fp32_tf32_off": time_reference_gpu(cfg, sd, dev, min(B, 2), 2, "fp32")}
+    if world == 1 and not args.no_cpu_baseline:
+        # ---- CPU baseline: the unmodified reference forward on the host cores, ONE 6-s segment (~20-30 s of CPU);
+        # the same forward doubles as a full-size parity check of the GPU path ----
+        cores = os.cpu_count() or 1
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        ref, kind = reference_model(cfg, sd)
+        n = SEG if kind == "reference" else SEG // 4
+        mix = make_mixture(1, n)
+        cpu_forward(ref, make_mixture(1, SR // 2), cores)      # spin the thread pool up
+        want, dt = cpu_forward(ref, mix, cores)
+        with torch.no_grad():
+            got = model(mix.to(dev))
+        import oracle
+        worst = min(oracle.si_sdr_db(got[k].cpu(), want[k]) for k in want)
+        err = max(float((got[k].cpu() - want[k]).abs().max()) for k in want)
+        line["cpu_baseline"] = {"value": n / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                                "sample": f"one {n / SR:.2f}-s mono segment, batch 1, fp32, {dt:.1f} s"}
+        line["parity"] = {"vs": f"cpu {kind}, same weights and input, {n / SR:.2f}-s segment",
+                          "worst_si_sdr_db": worst, "max_abs": err}
+    elif world > 1:
+        line["cpu_baseline"] = None   # N = 1 only (see the module docstring)
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -87,6 +87,11 @@ int tfl_rms_group_norm(const tfl_plan* plan, const void* packed, int layer, int 
 int tfl_conv_swiglu_ffn(const tfl_plan* plan, const void* packed, int layer, int axis, int ffn_index,
                         float* x, int batch, int n_frames, int n_freq, void* workspace, size_t ws_bytes,
                         int precision, tfl_stream_t stream);
+/* Same sub-block, out of place: y = x + ConvSwiGLU(RMSGroupNorm(x)); x and y must not overlap.  This is the form the
+ * bf16 kernel computes natively (tfl_blocks ping-pongs two residual buffers); the in-place call above adds a copy. */
+int tfl_conv_swiglu_ffn_out(const tfl_plan* plan, const void* packed, int layer, int axis, int ffn_index,
+                            const float* x, float* y, int batch, int n_frames, int n_freq, void* workspace,
+                            size_t ws_bytes, int precision, tfl_stream_t stream);
 /* :452-456 -> :504-559.  In place: x += MHSA_RoPE(RMSGroupNorm(x)) along `axis`. */
 int tfl_rope_attn(const tfl_plan* plan, const void* packed, int layer, int axis, float* x, int batch,
                   int n_frames, int n_freq, void* workspace, size_t ws_bytes, int precision,
@@ -111,12 +116,15 @@ int tfl_separator_forward(const tfl_plan* plan, const void* packed, const float*
                           int n_frames, int n_freq, float* est, void* workspace, size_t ws_bytes,
                           int precision, tfl_stream_t stream);
 /* Full-track stitch (new): track[S, n_track] += window(seg) * seg_audio[S, B, seg_len]
- * for segments seg_index0 .. seg_index0 + B - 1 of n_seg_total at 50 % overlap. */
+ * for segments seg_index0 .. seg_index0 + B - 1 of n_seg_total at 50 % overlap.  `track` holds the samples
+ * [track_origin, track_origin + n_track) of the full track (a rank's own range plus its halo; 0 = whole track). */
 int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, int seg_index0,
-                    int n_seg_total, float* track, int64_t n_track, tfl_stream_t stream);
+                    int n_seg_total, float* track, int64_t n_track, int64_t track_origin, tfl_stream_t stream);
 
-/* Diagnostic: every mbarrier wait in the tcgen05 kernels is bounded.  out5 = {timed_out, block, thread, shared-memory
- * address of the barrier, parity} of the first wait that expired since the last reset (device synchronising call). */
+/* Every mbarrier wait in the tcgen05 kernels is bounded (~2 s).  A wait that expires is a pipeline protocol error: the
+ * kernel records {1, block, thread, shared-memory address of the barrier, parity} in a host-mapped record and traps, so
+ * the launch fails loudly (cudaErrorLaunchFailed at the next synchronising call) and every later tfl_* entry point
+ * returns an error naming the record.  This call copies the record to out5 (no device access) and optionally clears it. */
 int tfl_debug_timeout(uint32_t* out5, int reset);
 
 /* BandSplitModule.band_split, standalone/bslocoformer_separator.py:241-254.  spec [B, M, T, F, 2] -> x [B, T, nb, C].

@@ -33,13 +33,14 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_enc_conv_gln": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     "tfl_rms_group_norm": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P]),
     "tfl_conv_swiglu_ffn": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _Z, _I, _P]),
+    "tfl_conv_swiglu_ffn_out": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "tfl_rope_attn": (_I, [_P, _P, _I, _I, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "tfl_dec_conv": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "tfl_istft_ola": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "tfl_blocks": (_I, [_P, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "tfl_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),
     "tfl_separator_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _I, _P]),
-    "tfl_segment_ola": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "tfl_segment_ola": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _L, _P]),
     "tfl_bs_band_split": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tfl_bs_band_decode": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "tfl_debug_set_option": (_I, [_I, _I]),

@@ -2,6 +2,7 @@
 
     python -m mss_tf_locoformer_b200.build [--force] [-v]
 """
+import glob
 import os
 import subprocess
 import sys
@@ -10,7 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtfl_b200.so")
 SOURCES = ["tfl_api.cu"]
-HEADERS = ["common.cuh", "kernels_f32.cuh", "kernels_tc.cuh", "kernels_attn.cuh", "kernels_attn2.cuh", "kernels_bs.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "tfl.h")]
+
+
+def _inputs():
+    """Every file the library is compiled from (the staleness check must see ALL kernels: a glob, not a list)."""
+    return (glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+            [os.path.join(HERE, "..", "include", "tfl.h")])
+
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -19,7 +27,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in _inputs())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

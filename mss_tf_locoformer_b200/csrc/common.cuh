@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -30,12 +31,20 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-extern unsigned long long g_launches;  // kernels launched by this library since load (bench.py's gpu_launches)
-#define TFL_LAUNCH_CHECK()          \
-  do {                              \
-    ++::tfl::g_launches;            \
-    TFL_CUDA(cudaGetLastError());   \
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library since load (bench.py's gpu_launches)
+#define TFL_LAUNCH_CHECK()                                        \
+  do {                                                            \
+    ::tfl::g_launches.fetch_add(1, std::memory_order_relaxed);    \
+    TFL_CUDA(cudaGetLastError());                                 \
   } while (0)
+
+// Opt in to > 48 KB of dynamic shared memory.  The attribute belongs to the (device, function) pair, so it is set on
+// every launch of the calling thread's current device instead of being cached per thread (a host-only driver call).
+template <class Kernel>
+inline cudaError_t opt_in_smem(Kernel kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 // Maps (sequence s, position p) of one Locoformer path onto the channels-last residual
 // stream x[B, Tf, F, C] without materialising the reference's transposes

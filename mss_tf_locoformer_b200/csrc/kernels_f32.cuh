@@ -553,16 +553,18 @@ __global__ void __launch_bounds__(256, 2) dec_conv_kernel(const float* __restric
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) segment_ola_kernel(const float* __restrict__ seg, int n_src, int batch,
                                                           int seg_len, int seg_index0, int n_seg_total,
-                                                          float* __restrict__ track, long long n_track) {
+                                                          float* __restrict__ track, long long n_track,
+                                                          long long track_origin) {
   const int b = blockIdx.y, src = blockIdx.z;
   const int gi = seg_index0 + b;
-  const long long start = (long long)gi * (seg_len >> 1);
+  const long long start = (long long)gi * (seg_len >> 1) - track_origin;   // `track` starts at sample track_origin
   const float* in = seg + ((size_t)src * batch + b) * seg_len;
   float* out = track + (size_t)src * n_track;
   const int half = seg_len >> 1;
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < seg_len; m += gridDim.x * blockDim.x) {
     const long long t = start + m;
     if (t >= n_track) break;
+    if (t < 0) continue;
     float w = 0.5f - 0.5f * cospif(2.0f * (float)m / (float)seg_len);
     if ((gi == 0 && m < half) || (gi == n_seg_total - 1 && m >= half)) w = 1.f;
     atomicAdd(&out[t], w * in[m]);  // two addends per sample at most: order-independent in fp32

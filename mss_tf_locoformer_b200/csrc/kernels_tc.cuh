@@ -796,12 +796,8 @@ inline int tc_ffn(const tfl_plan* pl, const char* packed, int layer, int axis, i
     p.img = packed + f.tc2;
     return tc_ffn2_dispatch(pl, p, c.emb_dim, f.hidden, c.conv_kernel, c.num_groups, st);
   }
-  static thread_local uint32_t smem_set[2] = {0, 0};
-  if (g.smem_bytes > smem_set[g.NT - 1]) {
-    if (g.NT == 2) TFL_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    else TFL_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    smem_set[g.NT - 1] = g.smem_bytes;
-  }
+  if (g.NT == 2) TFL_CUDA(opt_in_smem(ffn_tc_kernel<2>, g.smem_bytes));
+  else TFL_CUDA(opt_in_smem(ffn_tc_kernel<1>, g.smem_bytes));
   const int n_pairs = (p.n_tiles + g.NT - 1) / g.NT;
   const int grid = n_pairs < pl->sm_count ? n_pairs : pl->sm_count;
   if (g.NT == 2) ffn_tc_kernel<2><<<grid, g.threads, g.smem_bytes, st>>>(p, g);

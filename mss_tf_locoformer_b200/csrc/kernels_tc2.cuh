@@ -161,16 +161,7 @@ __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parit
 #pragma unroll 1
     for (int i = 0; i < 64; ++i)
       if (mbar_try_wait_cluster(bar, parity)) return;
-    const long long waited = clock64() - t0;
-    if (waited < (1LL << 21)) continue;
-    if (*(volatile unsigned int*)&g_wait_timeout[0] != 0) return;
-    if (waited > 1000000000LL) {
-      if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
-        g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
-        __threadfence();
-      }
-      return;
-    }
+    if (clock64() - t0 > WAIT_LIMIT_CLOCKS) wait_expired(bar, parity);
   }
 }
 __device__ __forceinline__ void mma2_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
@@ -639,11 +630,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
 inline int tc_ffn2_launch(const tfl_plan* pl, const FfnTcParams& p0, const Ffn2Geom& g, cudaStream_t st) {
   FfnTcParams p = p0;
   p.n_tiles = (int)((p.R + g.TS - 1) / g.TS);
-  static thread_local uint32_t smem_set = 0;
-  if (g.smem_bytes > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(ffn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    smem_set = g.smem_bytes;
-  }
+  TFL_CUDA(opt_in_smem(ffn_tc2_kernel, g.smem_bytes));
   const int n_pairs = (p.n_tiles + 1) / 2;
   int clusters = pl->sm_count / 2;
   if (n_pairs < clusters) clusters = n_pairs;

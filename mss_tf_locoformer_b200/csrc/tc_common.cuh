@@ -57,27 +57,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU.  The first wait that times out records
-// (block, thread, barrier address, parity) in g_wait_timeout and raises an abort flag; every later wait returns
-// at once, so the kernel drains (with garbage results) and the host reports the error (tfl_debug_timeout).
+// Bounded wait: a protocol bug must never hang the GPU, and must never pass silently either.  The first wait that
+// expires records (block, thread, barrier address, parity) in g_wait_timeout AND in a host-mapped copy of that record
+// (g_timeout_host, installed per device by the library; it survives the trap), then traps: the launch fails, the
+// context reports cudaErrorLaunchFailed at the next synchronising call, and every later tfl_* entry point returns an
+// error naming the record (tfl_api.cu: timeout_pending).
 __device__ unsigned int g_wait_timeout[5] = {0, 0, 0, 0, 0};
+__device__ unsigned int* g_timeout_host = nullptr;
+constexpr long long WAIT_LIMIT_CLOCKS = 4000000000LL;         // ~2 s at 1.9 GHz; legitimate waits are < 1 ms
+__device__ __noinline__ void wait_expired(uint32_t bar, uint32_t parity) {
+  if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
+    g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
+    unsigned int* h = g_timeout_host;
+    if (h != nullptr) {
+      h[1] = blockIdx.x; h[2] = threadIdx.x; h[3] = bar; h[4] = parity;
+      __threadfence_system();
+      *(volatile unsigned int*)h = 1u;
+    }
+    __threadfence_system();
+  }
+  __trap();
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   for (;;) {
 #pragma unroll 1
     for (int i = 0; i < 64; ++i)
       if (mbar_try_wait(bar, parity)) return;
-    const long long waited = clock64() - t0;
-    if (waited < (1LL << 21)) continue;        // keep global memory out of the polling loop (a ~1.5 k clk load per 64 polls
-                                               // sat between every producer -> consumer handoff of the pipelines)
-    if (*(volatile unsigned int*)&g_wait_timeout[0] != 0) return;
-    if (waited > 1000000000LL) {
-      if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
-        g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
-        __threadfence();
-      }
-      return;
-    }
+    // (no global memory in the polling loop: a ~1.5 k clk load per 64 polls sat between every producer -> consumer
+    // handoff of the pipelines)
+    if (clock64() - t0 > WAIT_LIMIT_CLOCKS) wait_expired(bar, parity);
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels_f32.cuh"
@@ -17,9 +18,40 @@
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static int g_options[TFL_OPT_COUNT] = {2, 2, 0, 0};   // tfl_debug_set_option
-int tfl_option(int key) { return g_options[key]; }
-unsigned long long g_launches = 0;
+static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {0}};   // tfl_debug_set_option
+int tfl_option(int key) { return g_options[key].load(std::memory_order_relaxed); }
+std::atomic<unsigned long long> g_launches{0};
+
+// ---- per-device one-time setup: the host-mapped record of an expired bounded wait (tc_common.cuh) -------------------
+static std::mutex g_init_mu;
+static unsigned int* g_timeout_rec = nullptr;      // pinned, mapped, portable; 5 words (flag, block, thread, barrier, parity)
+static bool g_dev_ready[64] = {false};
+static int ensure_device_ready() {
+  int dev = 0;
+  TFL_CUDA(cudaGetDevice(&dev));
+  TFL_CHECK(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_init_mu);
+  if (g_dev_ready[dev]) return 0;
+  if (g_timeout_rec == nullptr) {
+    void* h = nullptr;
+    TFL_CUDA(cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(h, 0, 64);
+    g_timeout_rec = (unsigned int*)h;
+  }
+  unsigned int* dptr = nullptr;
+  TFL_CUDA(cudaHostGetDevicePointer((void**)&dptr, g_timeout_rec, 0));
+  TFL_CUDA(cudaMemcpyToSymbol(tc::g_timeout_host, &dptr, sizeof(dptr)));
+  g_dev_ready[dev] = true;
+  return 0;
+}
+// An mbarrier wait of an EARLIER launch expired (the kernel trapped): refuse to go on, say where.
+static int timeout_pending() {
+  const volatile unsigned int* r = g_timeout_rec;
+  TFL_CHECK(r == nullptr || r[0] == 0,
+            "a bounded mbarrier wait expired in an earlier launch (block %u, thread %u, barrier smem address 0x%x, parity %u): "
+            "pipeline protocol error, results are invalid", r[1], r[2], r[3], r[4]);
+  return 0;
+}
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -105,9 +137,9 @@ using namespace tfl;
 
 extern "C" {
 
-int tfl_version(void) { return 100; }
+int tfl_version(void) { return 200; }
 const char* tfl_last_error(void) { return g_err; }
-uint64_t tfl_launch_count(void) { return g_launches; }
+uint64_t tfl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int tfl_plan_create(const tfl_config* cfg, tfl_plan** out) {
   TFL_CHECK(cfg != nullptr && out != nullptr, "null argument");
@@ -220,7 +252,7 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
 // ---- workspace ------------------------------------------------------------------------
 namespace tfl {
 struct Workspace {
-  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, tc, qkv_img, o_img, rope, total;
+  size_t spec, x, xn, hid, qkv, o, est, gln_part, gln_stats, prefix, tc, qkv_img, o_img, rope, total;
   int gln_blocks;
 };
 static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int precision) {
@@ -237,12 +269,15 @@ static Workspace plan_workspace(const tfl_plan* pl, int B, int Tf, int F, int pr
   w.gln_blocks = pl->sm_count * 2;
   w.gln_part = take((size_t)B * w.gln_blocks * 2 * sizeof(double));
   w.gln_stats = take((size_t)B * 2 * sizeof(float));
-  w.xn = take(N * C * sizeof(float));
-  const size_t hid_rows_f = (size_t)B * Tf * (F + K - 1), hid_rows_t = (size_t)B * F * (Tf + K - 1);
-  const size_t hid_rows = hid_rows_f > hid_rows_t ? hid_rows_f : hid_rows_t;
-  if (precision == TFL_PRECISION_FP32) w.hid = take(hid_rows * Hmax * sizeof(float));
-  w.qkv = take(N * 3 * A * sizeof(float));
-  w.o = take(N * A * sizeof(float));
+  w.prefix = off;   // everything above is precision-independent (tfl_enc_conv_gln uses only this part)
+  if (precision == TFL_PRECISION_FP32) {   // CUDA-core path: normalised copy, hidden activation, q|k|v, attention output
+    const size_t hid_rows_f = (size_t)B * Tf * (F + K - 1), hid_rows_t = (size_t)B * F * (Tf + K - 1);
+    const size_t hid_rows = hid_rows_f > hid_rows_t ? hid_rows_f : hid_rows_t;
+    w.xn = take(N * C * sizeof(float));
+    w.hid = take(hid_rows * Hmax * sizeof(float));
+    w.qkv = take(N * 3 * A * sizeof(float));
+    w.o = take(N * A * sizeof(float));
+  }
   w.tc = take(tc_workspace_bytes(pl, B, Tf, F));
   if (precision == TFL_PRECISION_BF16) {  // 128-row bf16 tile images of q|k|v and of the attention output
     const size_t HDP = (size_t)(pl->head_dim + 15) / 16 * 16;
@@ -354,7 +389,6 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
   __nv_bfloat16* oimg = (__nv_bfloat16*)(wsp + ws.o_img);
   float2* rope = (float2*)(wsp + ws.rope);
   const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
-  static thread_local uint32_t smem_set[5] = {0, 0, 0, 0, 0};
   if (c.rope) {
     rope_table_kernel<<<(L * (HDP / 2) + 255) / 256, 256, 0, st>>>(rope, (const float*)(packed + p.rope), L, hd / 2, HDP / 2);
     TFL_LAUNCH_CHECK();
@@ -366,10 +400,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     q.C = C; q.G = c.num_groups; q.L = L; q.NTL = NTL; q.nseq = nseq; q.heads = heads; q.hd = hd; q.HDP = HDP;
     q.NPART = NPART; q.n_tiles = nseq * NTL; q.qscale = 1.4426950408889634f / sqrtf((float)hd);
     const uint32_t smem = 3u * C * NPART * 2 + 3u * C * 256 + C * 4 + 256;
-    if (smem > smem_set[0]) {
-      TFL_CUDA(cudaFuncSetAttribute(qkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[0] = smem;
-    }
+    TFL_CUDA(opt_in_smem(qkv_tc_kernel, smem));
     const int grid = q.n_tiles < pl->sm_count ? q.n_tiles : pl->sm_count;
     qkv_tc_kernel<<<grid, QKV_THREADS, smem, st>>>(q);
     TFL_LAUNCH_CHECK();
@@ -377,18 +408,17 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
   {
     // query rows that do not fill a tile run on CUDA cores when there are only a few of them (1025 = 8*128 + 1,
     // 259 = 2*128 + 3): a mostly empty tensor-core tile costs as much as a full one
-    const int tail_q = (L > 128 && L % 128 != 0 && L % 128 <= 8) ? L % 128 : 0;
+    const int Lpad = (L + 31) & ~31;
+    const size_t tsm = (size_t)8 * Lpad * sizeof(float);      // score rows of the 8 warps of a tail-row block
+    const int tail_q = (L > 128 && L % 128 != 0 && L % 128 <= 8 && tsm <= 160 * 1024) ? L % 128 : 0;
     AttnTcParams ap;
     ap.qkv = qkv; ap.o = oimg; ap.nseq = nseq; ap.heads = heads; ap.L = L; ap.NTL = NTL; ap.HDP = HDP;
     ap.NQT = tail_q ? L / 128 : NTL;
     ap.NU = (L + 63) / 64;
     ap.NP = (ap.NQT + 1) / 2; ap.n_items = nseq * heads * ap.NP;
-    if (g_options[TFL_OPT_ATTN_KERNEL] == 1) {
+    if (tfl_option(TFL_OPT_ATTN_KERNEL) == 1) {
       const uint32_t smem = attn_tc_smem(HDP);
-      if (smem > smem_set[1]) {
-        TFL_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[1] = smem;
-      }
+      TFL_CUDA(opt_in_smem(attn_tc_kernel, smem));
       const int grid = ap.n_items < pl->sm_count ? ap.n_items : pl->sm_count;
       attn_tc_kernel<<<grid, 352, smem, st>>>(ap);
     } else {
@@ -402,27 +432,17 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       const uint32_t smem = attn2_smem(HDP, a2.HG, &a2.NS);
       TFL_CHECK(a2.NS >= 2, "attention K/V ring does not fit in shared memory");
       auto kern = HDP == 16 ? attn_tc2_kernel<1> : attn_tc2_kernel<2>;
-      const int si = HDP == 16 ? 3 : 4;
-      if (smem > smem_set[si]) {
-        TFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[si] = smem;
-      }
+      TFL_CUDA(opt_in_smem(kern, smem));
       const int grid = a2.n_items < pl->sm_count ? a2.n_items : pl->sm_count;
       kern<<<grid, ATT2_THREADS, smem, st>>>(a2);
     }
     TFL_LAUNCH_CHECK();
     if (tail_q) {
-      const int Lpad = (L + 31) & ~31;
-      int rg = 1;   // rows sharing one pass over K / V (RG = 3 measured slower: 192 accumulator / query registers per lane)
-      while (rg > 1 && (size_t)8 * rg * Lpad * sizeof(float) > 48 * 1024) --rg;
-      const size_t tsm = (size_t)8 * rg * Lpad * sizeof(float);
-      TFL_CHECK(tsm <= 48 * 1024, "sequence too long for the attention tail-row kernel");
-      const long long warps = (long long)nseq * heads * ((tail_q + rg - 1) / rg);
+      const long long warps = (long long)nseq * heads * tail_q;
       long long blocks = (warps + 7) / 8;
       if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
-      if (rg == 3) attn_tail_rows_kernel<3><<<(int)blocks, 256, tsm, st>>>(ap, ap.NQT * 128);
-      else if (rg == 2) attn_tail_rows_kernel<2><<<(int)blocks, 256, tsm, st>>>(ap, ap.NQT * 128);
-      else attn_tail_rows_kernel<1><<<(int)blocks, 256, tsm, st>>>(ap, ap.NQT * 128);
+      TFL_CUDA(opt_in_smem(attn_tail_rows_kernel<1>, tsm));
+      attn_tail_rows_kernel<1><<<(int)blocks, 256, tsm, st>>>(ap, ap.NQT * 128);
       TFL_LAUNCH_CHECK();
     }
   }
@@ -431,10 +451,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     pp.oimg = oimg; pp.wimg = packed + p.tc_wo; pp.x = x; pp.map = xmap;
     pp.C = C; pp.AP = NPART; pp.L = L; pp.NTL = NTL; pp.n_tiles = nseq * NTL;
     const uint32_t smem = (uint32_t)NPART * C * 2 + PROJ_STAGES * (uint32_t)NPART * 256 + 2 * PROJ_STG_BYTES + 256;
-    if (smem > smem_set[2]) {
-      TFL_CUDA(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[2] = smem;
-    }
+    TFL_CUDA(opt_in_smem(proj_tc_kernel, smem));
     const int grid = pp.n_tiles < pl->sm_count ? pp.n_tiles : pl->sm_count;
     proj_tc_kernel<<<grid, 320, smem, st>>>(pp);
     TFL_LAUNCH_CHECK();
@@ -478,7 +495,8 @@ static int check_common(const tfl_plan* pl, const void* packed, int B, int Tf, i
   TFL_CHECK(pl != nullptr && packed != nullptr, "null plan / packed weights");
   TFL_CHECK(B >= 1 && Tf >= 1 && F >= 1, "empty input (batch %d, frames %d, bins %d)", B, Tf, F);
   TFL_CHECK(precision == TFL_PRECISION_FP32 || precision == TFL_PRECISION_BF16, "unknown precision %d", precision);
-  return 0;
+  if (ensure_device_ready()) return -1;
+  return timeout_pending();
 }
 }  // namespace tfl
 
@@ -496,6 +514,7 @@ int tfl_stft(const tfl_plan* pl, const void* packed, const float* audio, int B, 
   TFL_CHECK(T > c.n_fft / 2, "reflect padding needs more than n_fft/2 = %d samples (got %d)", c.n_fft / 2, T);
   const int Tf = 1 + T / c.hop;
   const char* base = (const char*)packed;
+  TFL_CUDA(opt_in_smem(stft_kernel, c.n_fft * sizeof(float2)));
   stft_kernel<<<dim3(Tf, B), 256, c.n_fft * sizeof(float2), (cudaStream_t)stream>>>(
       audio, T, c.n_fft, ilog2(c.n_fft), c.hop, Tf, (const float2*)(base + pl->lay.twiddle),
       (const float*)(base + pl->lay.window), spec);
@@ -508,7 +527,7 @@ int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, 
   if (check_common(pl, packed, B, Tf, F, 0)) return -1;
   TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv encoder");
   const Workspace ws = plan_workspace(pl, B, Tf, F, 0);  // only the precision-independent prefix is used here
-  TFL_CHECK(workspace && ws_bytes >= ws.xn, "workspace too small (%zu < %zu)", ws_bytes, ws.xn);
+  TFL_CHECK(workspace && ws_bytes >= ws.prefix, "workspace too small (%zu < %zu)", ws_bytes, ws.prefix);
   const tfl_config& c = pl->cfg;
   const char* base = (const char*)packed;
   char* wsp = (char*)workspace;
@@ -559,6 +578,23 @@ int tfl_conv_swiglu_ffn(const tfl_plan* pl, const void* packed, int layer, int a
                  (cudaStream_t)stream);
 }
 
+int tfl_conv_swiglu_ffn_out(const tfl_plan* pl, const void* packed, int layer, int axis, int ffn_index, const float* x,
+                            float* y, int B, int Tf, int F, void* workspace, size_t ws_bytes, int precision,
+                            tfl_stream_t stream) {
+  if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  TFL_CHECK(x != nullptr && y != nullptr && x != y, "x and y must be distinct buffers");
+  TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer/axis");
+  TFL_CHECK(ffn_index >= 0 && ffn_index < pl->n_ffn, "bad ffn index %d", ffn_index);
+  const Workspace ws = plan_workspace(pl, B, Tf, F, precision);
+  TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
+  if (precision == TFL_PRECISION_BF16)
+    return tc_ffn(pl, (const char*)packed, layer, axis, ffn_index, const_cast<float*>(x), y, B, Tf, F, (cudaStream_t)stream);
+  TFL_CUDA(cudaMemcpyAsync(y, x, (size_t)B * Tf * F * pl->cfg.emb_dim * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return ffn_f32(pl, (const char*)packed, layer, axis, ffn_index, y, Dims{B, Tf, F}, ws, (char*)workspace,
+                 (cudaStream_t)stream);
+}
+
 int tfl_rope_attn(const tfl_plan* pl, const void* packed, int layer, int axis, float* x, int B, int Tf, int F,
                   void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
   if (check_common(pl, packed, B, Tf, F, precision)) return -1;
@@ -576,11 +612,7 @@ int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, 
   TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv decoder");
   const int C = pl->cfg.emb_dim;
   const size_t smem = (size_t)9 * C * 8 * sizeof(float);
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(dec_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  TFL_CUDA(opt_in_smem(dec_conv_kernel, smem));
   const long long n_pos = (long long)B * Tf * F;
   const char* base = (const char*)packed;
   long long blocks = ((long long)B * Tf * ((F + DEC_P - 1) / DEC_P) + 7) / 8;   // one warp per group of DEC_P bins
@@ -600,11 +632,7 @@ int tfl_istft_ola(const tfl_plan* pl, const void* packed, const float* est, int 
   TFL_CHECK(B >= 1 && Tf >= 1 && T >= 1, "empty input");
   const char* base = (const char*)packed;
   const size_t smem = (size_t)c.n_fft * sizeof(float2) + (size_t)2 * c.hop * sizeof(float);
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  TFL_CUDA(opt_in_smem(istft_ola_kernel, smem));
   dim3 grid((T + c.hop - 1) / c.hop, c.n_src, B);
   istft_ola_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(est, c.n_src, Tf, c.n_fft, ilog2(c.n_fft), c.hop, T,
                                                               (const float2*)(base + pl->lay.twiddle),
@@ -655,13 +683,13 @@ int tfl_forward(const tfl_plan* pl, const void* packed, const float* mixture, in
 }
 
 int tfl_segment_ola(const float* seg_audio, int n_src, int B, int seg_len, int seg_index0, int n_seg_total,
-                    float* track, int64_t n_track, tfl_stream_t stream) {
+                    float* track, int64_t n_track, int64_t track_origin, tfl_stream_t stream) {
   TFL_CHECK(seg_audio && track, "null argument");
   TFL_CHECK(n_src >= 1 && B >= 1 && seg_len >= 2 && seg_len % 2 == 0, "bad segment shape");
   TFL_CHECK(seg_index0 >= 0 && seg_index0 + B <= n_seg_total, "segment index out of range");
   dim3 grid((seg_len + 255) / 256 < 296 ? (seg_len + 255) / 256 : 296, B, n_src);
   segment_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seg_audio, n_src, B, seg_len, seg_index0, n_seg_total,
-                                                             track, n_track);
+                                                             track, n_track, track_origin);
   TFL_LAUNCH_CHECK();
   return 0;
 }
@@ -671,11 +699,7 @@ int tfl_bs_band_split(const float* spec, int B, int M, int T, int F, int C, int 
   TFL_CHECK(spec && table && weights && x, "null argument");
   TFL_CHECK(B >= 1 && (M == 1 || M == 2) && T >= 1 && F >= 1 && C >= 1 && nb >= 1 && max_width >= 1, "bad band-split shape");
   const size_t smem = ((size_t)max_width * 2 * M * BS_TT + 64) * sizeof(float);
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(bs_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  TFL_CUDA(opt_in_smem(bs_split_kernel, smem));
   dim3 grid(nb, (T + BS_TT - 1) / BS_TT, B);
   bs_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(spec, M, T, F, C, nb, (const long long*)table, weights, x, 1e-5f);
   TFL_LAUNCH_CHECK();
@@ -688,11 +712,7 @@ int tfl_bs_band_decode(const float* x, const float* spec, int B, int M, int T, i
   TFL_CHECK(B >= 1 && (M == 1 || M == 2) && T >= 1 && F >= 1 && C >= 1 && nb >= 1 && n_src >= 1, "bad band-decode shape");
   const size_t smem = ((size_t)9 * C * BS_TT + 64) * sizeof(float);
   TFL_CHECK(smem <= (size_t)TC_SMEM_MAX, "emb_dim too large for the band decoder");
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    TFL_CUDA(cudaFuncSetAttribute(bs_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  TFL_CUDA(opt_in_smem(bs_decode_kernel, smem));
   dim3 grid(nb, (T + BS_TT - 1) / BS_TT, B);
   bs_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, spec, M, T, F, C, nb, n_src, (const long long*)table, weights,
                                                               est, masking, 1e-5f);
@@ -702,7 +722,7 @@ int tfl_bs_band_decode(const float* x, const float* spec, int B, int M, int T, i
 
 int tfl_debug_set_option(int key, int value) {
   TFL_CHECK(key >= 0 && key < TFL_OPT_COUNT, "unknown option %d", key);
-  g_options[key] = value;
+  g_options[key].store(value, std::memory_order_relaxed);
   return 0;
 }
 
@@ -714,10 +734,13 @@ int tfl_debug_set_trace(void* device_buffer) {
 
 int tfl_debug_timeout(uint32_t* out5, int reset) {
   TFL_CHECK(out5 != nullptr, "null argument");
-  TFL_CUDA(cudaMemcpyFromSymbol(out5, tc::g_wait_timeout, 5 * sizeof(uint32_t)));
-  if (reset) {
+  std::lock_guard<std::mutex> lock(g_init_mu);
+  for (int i = 0; i < 5; ++i) out5[i] = g_timeout_rec != nullptr ? g_timeout_rec[i] : 0u;
+  if (reset && g_timeout_rec != nullptr) {
+    for (int i = 0; i < 5; ++i) g_timeout_rec[i] = 0u;
     const uint32_t zero[5] = {0, 0, 0, 0, 0};
-    TFL_CUDA(cudaMemcpyToSymbol(tc::g_wait_timeout, zero, sizeof(zero)));
+    (void)cudaMemcpyToSymbol(tc::g_wait_timeout, zero, sizeof(zero));   // fails after a trap (dead context): ignored
+    (void)cudaGetLastError();
   }
   return 0;
 }

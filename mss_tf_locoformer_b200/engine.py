@@ -212,6 +212,19 @@ class Engine:
                                                Tf, F, ws.data_ptr(), ws.numel(), precision, _stream()))
         return x
 
+    def ffn_out(self, layer: int, axis: int, index: int, x: torch.Tensor, y: torch.Tensor, precision: int) -> torch.Tensor:
+        """Out of place on channels-last [B, Tf, F, C]: y = x + FFN(norm(x)) along ``axis`` (x, y distinct)."""
+        _require_cuda(x, "x")
+        _require_cuda(y, "y")
+        if not (x.is_contiguous() and y.is_contiguous()) or x.shape != y.shape:
+            raise ValueError("x and y must be contiguous tensors of the same shape")
+        B, Tf, F, _ = x.shape
+        ws = self.workspace(B, Tf, F, precision, x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.tfl_conv_swiglu_ffn_out(self.plan, self.packed.data_ptr(), layer, axis, index, x.data_ptr(),
+                                                   y.data_ptr(), B, Tf, F, ws.data_ptr(), ws.numel(), precision, _stream()))
+        return y
+
     def attn_(self, layer: int, axis: int, x: torch.Tensor, precision: int) -> torch.Tensor:
         """In place on channels-last x [B, Tf, F, C]: x += MHSA(norm(x)) along ``axis``."""
         _require_cuda(x, "x")
@@ -223,14 +236,15 @@ class Engine:
         return x
 
 
-def segment_ola(seg_audio: torch.Tensor, seg_index0: int, n_seg_total: int, track: torch.Tensor):
-    """track[S, n] += window * seg_audio[S, B, seg_len] for segments seg_index0.. (tfl_segment_ola)."""
+def segment_ola(seg_audio: torch.Tensor, seg_index0: int, n_seg_total: int, track: torch.Tensor, track_origin: int = 0):
+    """track[S, n] += window * seg_audio[S, B, seg_len] for segments seg_index0.. (tfl_segment_ola); ``track`` holds the
+    samples [track_origin, track_origin + n) of the full track."""
     _require_cuda(seg_audio, "seg_audio")
     S, B, L = seg_audio.shape
     lib = _lib.load()
     with torch.cuda.device(track.device):
         check(lib.tfl_segment_ola(seg_audio.contiguous().data_ptr(), S, B, L, seg_index0, n_seg_total, track.data_ptr(),
-                                  track.shape[-1], _stream()))
+                                  track.shape[-1], track_origin, _stream()))
     return track
 
 

@@ -35,3 +35,15 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(autouse=True)
+def _no_expired_waits(request):
+    """After every GPU test: no bounded mbarrier wait of the tcgen05 kernels may have expired (an expired wait traps
+    the kernel; the record lives in host memory, so this check is free and never touches the device)."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    from mss_tf_locoformer_b200.engine import debug_timeout
+    rec = debug_timeout(reset=False)
+    assert rec[0] == 0, f"a bounded mbarrier wait expired: block {rec[1]}, thread {rec[2]}, barrier 0x{rec[3]:x}, parity {rec[4]}"

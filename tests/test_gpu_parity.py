@@ -269,3 +269,50 @@ def test_ragged_lengths_fp32(pkg, n_samples):
     for k in want:
         assert got[k].shape == (1, n_samples)
         _check(got[k], want[k], what=f"T={n_samples}/{k}")
+
+
+def _track_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    import mss_tf_locoformer_b200 as m
+    from mss_tf_locoformer_b200.segments import separate_track
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg, sd, arr = load_golden("mss_hop2_macaron")
+        model = m.TFLocoformerMSS(**cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        track = _mixture(9000, 1)[0].cuda()
+        with torch.no_grad():
+            out = separate_track(model, track, seg_len=1024, batch=3)
+        ret[rank] = {k: v.cpu() for k, v in out.items()}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_full_track_two_gpus_nccl_matches_one_gpu(pkg):
+    """Halo exchange (NCCL send/recv) + all-gather of the own ranges on 2 GPUs == the single-GPU stitch: bit-exact
+    outside the halo between the two ranks, <= 1 ulp-level inside it (two addends summed in another order)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    from mss_tf_locoformer_b200.segments import separate_track
+    cfg, sd, arr, model = _mss(pkg, "mss_hop2_macaron")
+    track = _mixture(9000, 1)[0].cuda()
+    with torch.no_grad():
+        one = separate_track(model, track, seg_len=1024, batch=3)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_track_worker, args=(2, port, ret), nprocs=2, join=True)
+        res = dict(ret)
+    for r in (0, 1):
+        for k in one:
+            assert torch.allclose(res[r][k], one[k].cpu(), atol=1e-6, rtol=0), (r, k)
+    for k in one:
+        assert torch.equal(res[0][k], res[1][k])

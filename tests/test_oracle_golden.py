@@ -110,3 +110,21 @@ def test_stitch_is_partition_of_unity():
         assert torch.allclose(ident["a"], torch.arange(1, n + 1, dtype=torch.float32), atol=1e-4), (n, starts)
         assert torch.allclose(ident["b"], 2 * torch.arange(1, n + 1, dtype=torch.float32), atol=2e-4)
     assert len(oracle.segment_starts(10_584_000, 264_600)) == 79
+
+
+def test_rope_matches_independent_gptj_implementation():
+    """oracle/rope.py against an implementation nobody here wrote: transformers' GPT-J rotary embedding
+    (`create_sinusoidal_positions`, `rotate_every_two`, `apply_rotary_pos_emb`), which is the same published
+    convention rotary-embedding-torch follows for `RotaryEmbedding(dim).rotate_queries_or_keys` (interleaved pairs,
+    theta = 10000, positions from 0, whole head rotated).  rotary-embedding-torch==0.6.1 itself is absent from the image
+    (requirements.txt:23; `pip download` fails offline), so this is the strongest pin available for that boundary."""
+    gptj = pytest.importorskip("transformers.models.gptj.modeling_gptj")
+    from oracle import rope
+    for hd, L in ((32, 1025), (24, 517), (12, 259), (8, 50)):
+        g = torch.Generator().manual_seed(hd)
+        t = torch.randn(2, 4, L, hd, generator=g)                       # [B, H, L, hd]; the reference's layout
+        got = rope.rope_rotate(t, rope.rope_freqs(hd))
+        sincos = gptj.create_sinusoidal_positions(L, hd)               # [L, hd]: sin | cos
+        sin, cos = sincos[None, :, : hd // 2], sincos[None, :, hd // 2:]
+        want = gptj.apply_rotary_pos_emb(t.transpose(1, 2), sin, cos).transpose(1, 2)   # GPT-J wants [B, L, H, hd]
+        assert torch.allclose(got, want, atol=2e-5, rtol=0), float((got - want).abs().max())

@@ -22,13 +22,13 @@ def test_starts_and_partition_match_survey():
         assert segments.segment_starts(n, 64) == oracle.segment_starts(n, 64)
 
 
-def _cpu_ola(seg_out, i0, n_seg, acc):
+def _cpu_ola(seg_out, i0, n_seg, acc, origin=0):
     """CPU stand-in for tfl_segment_ola in host-logic tests (the product default is the CUDA kernel)."""
     s, b, length = seg_out.shape
     for k in range(b):
         gi = i0 + k
         w = oracle.segment_window(length, gi == 0, gi == n_seg - 1, seg_out.dtype)
-        start = gi * (length // 2)
+        start = gi * (length // 2) - origin
         acc[:, start:start + length] += seg_out[:, k] * w
 
 
@@ -55,13 +55,21 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("n,seg", [(1000, 64), (40, 64), (997, 128)])
-def test_two_rank_gloo_matches_single_process_oracle(n, seg):
-    world = 2
+def test_owned_ranges_tile_the_track():
+    for n_seg, world in ((79, 8), (79, 2), (3, 4), (1, 2), (10, 3)):
+        own = segments.owned_ranges(n_seg, 64, world)
+        total = (n_seg - 1) * 32 + 64
+        spans = [(a, b) for a, b in own if b > a]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+
+
+@pytest.mark.parametrize("n,seg,world", [(1000, 64, 2), (40, 64, 2), (997, 128, 2), (1000, 64, 3), (100, 64, 4)])
+def test_multi_rank_gloo_matches_single_process_oracle(n, seg, world):
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, _free_port(), n, seg, ret), nprocs=world, join=True)
-        assert dict(ret) == {0: True, 1: True}
+        assert dict(ret) == {r: True for r in range(world)}
 
 
 def test_single_process_path():
