@@ -433,6 +433,10 @@ inline uint32_t attn_tc_smem(int HDP) {
 //   warps 6-13: two epilogue groups, each owning half of the columns of every part
 // TMEM: three part accumulators (q, k, v) of NPART = heads * HDP columns used as a ring across tiles.
 // --------------------------------------------------------------------------------------------
+// MUFU approximations (~1 ulp): the operand they scale is rounded to bf16 (2^-9) right after
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 struct QkvTcParams {
   const float* x; SeqMap map; const float* gamma; float eps;
   const char* wimg;                 // [3 parts][C/8 chunks][NPART rows][8] bf16
@@ -452,9 +456,12 @@ __global__ void rope_table_kernel(float2* __restrict__ tab, const float* __restr
   tab[(size_t)f * L + j] = make_float2(cs, sn);           // frequency-major: the 32 rows of a warp read contiguously
 }
 
+// The q|k|v weight image carries the RMSGroupNorm gamma (column c of every row is multiplied by gamma[c]: the
+// producers of qkv_tc_kernel then only scale by 1 / rms) and, in the q part, the softmax pre-scale log2(e) / sqrt(hd)
+// (RoPE is a rotation, so scaling commutes with it): two multiplies per element less in the kernel's hot loops.
 __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* __restrict__ wo,
-                                   __nv_bfloat16* __restrict__ qimg, __nv_bfloat16* __restrict__ oimg, int C, int A,
-                                   int heads, int hd, int HDP) {
+                                   const float* __restrict__ gamma, __nv_bfloat16* __restrict__ qimg,
+                                   __nv_bfloat16* __restrict__ oimg, int C, int A, int heads, int hd, int HDP, float qscale) {
   const int NPART = heads * HDP;
   const int n_q = 3 * C * NPART, n_o = NPART * C;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_q + n_o; idx += gridDim.x * blockDim.x) {
@@ -462,7 +469,8 @@ __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* 
       const int part = idx / (C * NPART), e = idx % (C * NPART);
       const int chunk = e / (NPART * 8), n = (e / 8) % NPART, c = chunk * 8 + (e & 7);
       const int head = n / HDP, d = n % HDP;
-      qimg[idx] = __float2bfloat16_rn(d < hd ? wqkv[((size_t)part * A + head * hd + d) * C + c] : 0.f);
+      const float w = d < hd ? wqkv[((size_t)part * A + head * hd + d) * C + c] * gamma[c] * (part == 0 ? qscale : 1.f) : 0.f;
+      qimg[idx] = __float2bfloat16_rn(w);
     } else {           // wo image: [NPART/8][C rows][8]; row n = out channel, k = head*HDP + d  <-  wo[n][head*hd + d]
       const int e = idx - n_q;
       const int chunk = e / (C * 8), n = (e / 8) % C, k = chunk * 8 + (e & 7);
@@ -473,6 +481,9 @@ __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* 
 }
 
 constexpr int QKV_PRODUCER_WARPS = 8;
+#ifndef QKV_UF
+#define QKV_UF 8   // (8-row, group) units a producer lane keeps in flight (4: two round trips per tile, r01)
+#endif
 constexpr int QKV_THREADS = 32 * (2 + QKV_PRODUCER_WARPS + 8);
 
 __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
@@ -487,8 +498,6 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
   const int W_FULL = 0, A_FULL = 1, A_EMPTY = 4, D_FULL = 7, D_EMPTY = 10;   // A: 3 slots, D: 3 parts
   constexpr int NPROD = QKV_PRODUCER_WARPS * 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 16);
-  float* tab_gamma = reinterpret_cast<float*>(smem + off_tab);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) tab_gamma[i] = p.gamma[i];
   if (threadIdx.x == 0) {
     mbar_init(BAR(W_FULL), 1);
     for (int i = 0; i < 3; ++i) {
@@ -555,13 +564,18 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
         // two shuffles.  Eight items per thread and tile, four in flight at a time.
         const int r8 = lane >> 2, q4 = lane & 3;
         const int pw = warp - 2;                              // producer warp 0 .. QKV_PRODUCER_WARPS - 1
-        const int n_blk = 16 * G;                             // (8-row block, group) units per tile
+        // rows at or beyond ceil64(L) are never written to the images (see the epilogue): their A rows are left alone
+        const int rows_used = min(128, ((p.L + 63) & ~63) - jt * 128);
+        const int n_blk = ((rows_used + 7) >> 3) * G;          // (8-row block, group) units per tile
+        // QKV_UF units (2 x 128-bit loads each) in flight per lane: the producers are bound by global-load latency
+        // (ncu: the epilogue warps wait on D_FULL, the MMA warp on A_FULL), so a whole tile -- 64 units for 4 groups --
+        // is requested in ONE round trip of the 8 producer warps instead of two.
 #pragma unroll 1
-        for (int u0 = pw; u0 < n_blk; u0 += 4 * QKV_PRODUCER_WARPS) {
-          float4 v[4][2];
-          int rowi[4], grpi[4];
+        for (int u0 = pw; u0 < n_blk; u0 += QKV_UF * QKV_PRODUCER_WARPS) {
+          float4 v[QKV_UF][2];
+          int rowi[QKV_UF], grpi[QKV_UF];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < QKV_UF; ++u) {
             const int unit = u0 + u * QKV_PRODUCER_WARPS;
             const int rb = unit / G;
             grpi[u] = unit - rb * G;
@@ -573,21 +587,19 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
             v[u][1] = valid ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < QKV_UF; ++u) {
             if (u0 + u * QKV_PRODUCER_WARPS >= n_blk) continue;   // warp-uniform
             float ss = v[u][0].x * v[u][0].x + v[u][0].y * v[u][0].y + v[u][0].z * v[u][0].z + v[u][0].w * v[u][0].w +
                        v[u][1].x * v[u][1].x + v[u][1].y * v[u][1].y + v[u][1].z * v[u][1].z + v[u][1].w * v[u][1].w;
             ss += __shfl_xor_sync(0xffffffffu, ss, 1);
             ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+            const float inv = fast_rcp(fast_sqrt(ss) * rs + p.eps);
             const int c0 = grpi[u] * 32 + q4 * 8;
-            const float4 g0 = *reinterpret_cast<const float4*>(tab_gamma + c0);
-            const float4 g1 = *reinterpret_cast<const float4*>(tab_gamma + c0 + 4);
             uint4 pk;
-            pk.x = pack_bf16(v[u][0].x * inv * g0.x, v[u][0].y * inv * g0.y);
-            pk.y = pack_bf16(v[u][0].z * inv * g0.z, v[u][0].w * inv * g0.w);
-            pk.z = pack_bf16(v[u][1].x * inv * g1.x, v[u][1].y * inv * g1.y);
-            pk.w = pack_bf16(v[u][1].z * inv * g1.z, v[u][1].w * inv * g1.w);
+            pk.x = pack_bf16(v[u][0].x * inv, v[u][0].y * inv);
+            pk.y = pack_bf16(v[u][0].z * inv, v[u][0].w * inv);
+            pk.z = pack_bf16(v[u][1].x * inv, v[u][1].y * inv);
+            pk.w = pack_bf16(v[u][1].z * inv, v[u][1].w * inv);
             *reinterpret_cast<uint4*>(at + ((size_t)(c0 >> 3) * 128 + rowi[u]) * 16) = pk;
           }
         }
@@ -615,15 +627,14 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
             float ss = 0.f;
 #pragma unroll
             for (int d = 0; d < 8; ++d) ss += v[u][d].x * v[u][d].x + v[u][d].y * v[u][d].y + v[u][d].z * v[u][d].z + v[u][d].w * v[u][d].w;
-            const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+            const float inv = fast_rcp(fast_sqrt(ss) * rs + p.eps);
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
               if (4 * d < D) {
                 const int c0 = grpi[u] * D + 4 * d;
-                const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
                 uint2 pk;
-                pk.x = pack_bf16(v[u][d].x * inv * gm.x, v[u][d].y * inv * gm.y);
-                pk.y = pack_bf16(v[u][d].z * inv * gm.z, v[u][d].w * inv * gm.w);
+                pk.x = pack_bf16(v[u][d].x * inv, v[u][d].y * inv);
+                pk.y = pack_bf16(v[u][d].z * inv, v[u][d].w * inv);
                 *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + rowi[u]) * 16 + (c0 & 7) * 2) = pk;
               }
             }
@@ -641,15 +652,14 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
               const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
               ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             }
-          const float inv = 1.f / (sqrtf(ss) * rs + p.eps);
+          const float inv = fast_rcp(fast_sqrt(ss) * rs + p.eps);
           for (int d = 0; d < D; d += 4) {
             uint2 pk = make_uint2(0u, 0u);
             const int c0 = grp * D + d;
             if (valid) {
               const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
-              const float4 gm = *reinterpret_cast<const float4*>(tab_gamma + c0);
-              pk.x = pack_bf16(v.x * inv * gm.x, v.y * inv * gm.y);
-              pk.y = pack_bf16(v.z * inv * gm.z, v.w * inv * gm.w);
+              pk.x = pack_bf16(v.x * inv, v.y * inv);
+              pk.y = pack_bf16(v.z * inv, v.w * inv);
             }
             *reinterpret_cast<uint2*>(at + ((size_t)(c0 >> 3) * 128 + row) * 16 + (c0 & 7) * 2) = pk;
           }
@@ -699,7 +709,6 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
               const float ra = a * f.x - b * f.y, rb = b * f.x + a * f.y;
               a = ra; b = rb;
             }
-            if (part == 0) { a *= p.qscale; b *= p.qscale; }
             w[i >> 1] = pack_bf16(a, b);
           }
           __nv_bfloat16* dst = p.qkv + ((((size_t)part * p.nseq + s) * p.heads + head) * NTL + jt) * tile_elems +

@@ -42,9 +42,21 @@ struct Attn2Params {
   int n_items;
 };
 
+#ifndef ATT2_PREFETCH
+#define ATT2_PREFETCH 0   // 1: read the scores of half k + 1 back before the exp2 pass of half k (measured SLOWER, r02)
+#endif
 constexpr int ATT2_G = 4;
 constexpr int ATT2_MMA_WARPS = ATT2_G / 2;                           // one MMA warp per pair of groups
-constexpr int ATT2_THREADS = 32 * (4 * ATT2_G + ATT2_MMA_WARPS + 1);   // softmax warps, MMA warps, loader
+constexpr int ATT2_THREADS = 32 * (4 * ATT2_G + 4);   // softmax warps; one warpgroup of MMA warps, loader and an idle warp
+// Register split (setmaxnreg works on warpgroups of 4 consecutive warps and only re-splits the CTA's launch allocation
+// of 640 x 96 registers): 4 * 104 + 64 = 480 = 5 * 96.
+constexpr int ATT2_REGS_SOFTMAX = 104, ATT2_REGS_OTHER = 64;
+static_assert(4 * ATT2_REGS_SOFTMAX + ATT2_REGS_OTHER <= 480, "register budget of the CTA");
+#ifdef TFL_NO_SETMAXNREG   // bisecting aid: every warp keeps its launch allocation
+#define ATT2_SETMAXNREG(dir, n) do { } while (0)
+#else
+#define ATT2_SETMAXNREG(dir, n) asm volatile("setmaxnreg." dir ".sync.aligned.u32 %0;" ::"n"(n))
+#endif
 constexpr float ATT2_TH = 16.f;    // raise the softmax reference when a score exceeds it by more than this (log2 units)
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -94,16 +106,16 @@ inline uint32_t attn2_smem(int HDP, int HG, int* NS_out) {
   return fixed + (uint32_t)NS * stage;
 }
 
-// One 32-key half for one query row: scores (TMEM buffer bb) -> max -> [rare: raise m_ref, rescale O] -> exp2 ->
-// bf16 P written over the first 16 columns of the same buffer.  FULL: all 32 columns are keys; otherwise nkh are.
+// One 32-key half for one query row: scores s[] (already read from TMEM buffer bb) -> max -> [rare: raise m_ref, rescale
+// O] -> exp2 -> bf16 P written over the first 16 columns of the same buffer.  FULL: all 32 columns are keys; otherwise
+// nkh are.  The read-back itself is issued by the caller one half AHEAD (ATT2_PREFETCH): TMEM reads run at 64 B/clk per
+// SM -- 1024 clk for the 16 softmax warps of a half-step, the same as their 16 x 32 exp2 on the MUFU pipe -- so the
+// two have to overlap inside every warp, not only across warps.
 template <bool FULL>
-__device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int bb, uint32_t ph, uint32_t kk, int nkh, bool first,
-                                           int HDP, float& m_ref, float& l0, float& l1) {
+__device__ __forceinline__ void attn2_half(uint32_t (&s)[32], uint32_t tcol, uint32_t bgrp, int bb, uint32_t ph, uint32_t kk,
+                                           int nkh, bool first, int HDP, float& m_ref, float& l0, float& l1) {
   using namespace tc;
   constexpr uint32_t PV_DONE = 48;                               // byte offset inside the group's barrier block
-  uint32_t s[32];
-  tmem_ld32(tcol + bb * 32, s);
-  tc_wait_ld();
   if (!FULL) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) if (i >= nkh) s[i] = 0xff800000u;   // -inf: columns beyond the sequence
@@ -130,7 +142,7 @@ __device__ __forceinline__ void attn2_half(uint32_t tcol, uint32_t bgrp, int bb,
     for (int c0 = 0; c0 < HDP; c0 += 16) {
       uint32_t r[16];
       tmem_ld16(tcol + 96 + c0, r);
-      tc_wait_ld();
+      tc_wait_ld();                                              // (also drains a prefetched score read: harmless)
 #pragma unroll
       for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
       tmem_st16(tcol + 96 + c0, r);
@@ -204,8 +216,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
   };
   auto group_active = [&](int g, int h0, int q0) { return h0 + g / QG < p.heads && q0 + g % QG < p.NQT; };
 
-  if (warp == 4 * G + ATT2_MMA_WARPS) {
+  // (each role branch starts with its own setmaxnreg: ptxas bounds a region by the setmaxnreg that DOMINATES it)
+  if (warp == 4 * G + ATT2_MMA_WARPS + 1) {
+    // idle: only completes the warpgroup that gives its registers to the softmax groups
+    ATT2_SETMAXNREG("dec", ATT2_REGS_OTHER);
+  } else if (warp == 4 * G + ATT2_MMA_WARPS) {
     // ===================== loader =====================
+    ATT2_SETMAXNREG("dec", ATT2_REGS_OTHER);
     uint32_t kslot = 0, kph = 0, qph = 0;
     int n_local = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_local) {
@@ -249,6 +266,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
     // P_k V_k into the TMEM buffer that P_k occupies -- MMAs of one thread execute in issue order, so the overwrite
     // is safe), across item boundaries.  A softmax warp therefore always has its next scores waiting, and the four
     // warps of a group may drift up to two halves apart.  The whole warp runs the control flow; one lane issues.
+    ATT2_SETMAXNREG("dec", ATT2_REGS_OTHER);
     const int pw = warp - 4 * G;
     const uint32_t idesc_pv = instr_desc(128, HDP, /*b_mn_major=*/true);
     const uint32_t idesc_s_full = instr_desc(128, 32), idesc_s_last = instr_desc(128, (n_last + 15) & ~15);
@@ -385,6 +403,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
     }
   } else {
     // ===================== softmax groups =====================
+    ATT2_SETMAXNREG("inc", ATT2_REGS_SOFTMAX);
     const int g = warp >> 2;
     const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;
@@ -402,16 +421,52 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
       float m_ref = 0.f, l0 = 0.f, l1 = 0.f;
       const int n_full = n_last == 32 ? NH : NH - 1;
       int lb = 0; uint32_t lph = 0;                                // buffer / phase of the item's last half
+#if ATT2_PREFETCH
+      // Two score registers sets: the read-back of half k + 1 is issued (after its S_FULL) before the exp2 pass of
+      // half k, so TMEM-read time hides behind MUFU time inside the warp.  Loop unrolled by two to keep both sets in
+      // registers.  (bb, ph) describe half k; (nb, nph) half k + 1.
+      uint32_t sA[32], sB[32];
+      mbar_wait(bgrp + S_FULL + 8 * bb, ph);
+      tc_fence_after();
+      tmem_ld32(tcol + bb * 32, sA);
+#define ATT2_STEP(CUR, NXT)                                                                                         \
+      {                                                                                                             \
+        tc_wait_ld();                                                                                               \
+        const int nb = bb == 2 ? 0 : bb + 1;                                                                        \
+        const uint32_t nph = bb == 2 ? ph ^ 1 : ph;                                                                 \
+        if (k + 1 < NH) {                                                                                           \
+          mbar_wait(bgrp + S_FULL + 8 * nb, nph);                                                                   \
+          tc_fence_after();                                                                                         \
+          tmem_ld32(tcol + nb * 32, NXT);                                                                           \
+        }                                                                                                           \
+        if (k < n_full) attn2_half<true>(CUR, tcol, bgrp, bb, ph, kk, 32, k == 0, HDP, m_ref, l0, l1);              \
+        else attn2_half<false>(CUR, tcol, bgrp, bb, ph, kk, n_last, k == 0, HDP, m_ref, l0, l1);                    \
+        tc_fence_before();                                                                                          \
+        mbar_arrive(bgrp + P_FULL + 8 * bb);                                                                        \
+        lb = bb; lph = ph;                                                                                          \
+        bb = nb; ph = nph;                                                                                          \
+        ++k; ++kk;                                                                                                  \
+      }
+      for (int k = 0; k < NH;) {
+        ATT2_STEP(sA, sB)
+        if (k < NH) ATT2_STEP(sB, sA)
+      }
+#undef ATT2_STEP
+#else
       for (int k = 0; k < NH; ++k, ++kk) {
         mbar_wait(bgrp + S_FULL + 8 * bb, ph);
         tc_fence_after();
-        if (k < n_full) attn2_half<true>(tcol, bgrp, bb, ph, kk, 32, k == 0, HDP, m_ref, l0, l1);
-        else attn2_half<false>(tcol, bgrp, bb, ph, kk, n_last, k == 0, HDP, m_ref, l0, l1);
+        uint32_t s[32];
+        tmem_ld32(tcol + bb * 32, s);
+        tc_wait_ld();
+        if (k < n_full) attn2_half<true>(s, tcol, bgrp, bb, ph, kk, 32, k == 0, HDP, m_ref, l0, l1);
+        else attn2_half<false>(s, tcol, bgrp, bb, ph, kk, n_last, k == 0, HDP, m_ref, l0, l1);
         tc_fence_before();
         mbar_arrive(bgrp + P_FULL + 8 * bb);
         lb = bb; lph = ph;
         if (++bb == 3) { bb = 0; ph ^= 1; }
       }
+#endif
       // ---- all keys done: O / l -> this head's slice of the o image ----
       mbar_wait(bgrp + PV_DONE + 8 * lb, lph);
       tc_fence_after();

@@ -10,9 +10,13 @@
 //     although the tile count per weight pass halves;
 //   * the two SwiGLU groups alternate chunks; the group that takes chunk 0 of the next tile writes the previous tile
 //     out afterwards, while the other group already works on chunk 1.
-// Roles per CTA (16 warps):  0 / 2 loaders of the conv1d / transposed-conv weight rings (own half of every stage)
-// 1 / 3 leader: conv1d / transposed-conv MMAs, peer: relays "my half of the stage landed" to the leader
-// 4-7 A-tile producers   8-11 / 12-15 SwiGLU groups of even / odd chunks.
+// Roles per CTA (20 warps = five warpgroups; registers are re-split with setmaxnreg, see FFN2_REGS_*):
+//   0 / 2 loaders of the conv1d / transposed-conv weight rings (own half of every stage)
+//   1 / 3 leader: conv1d / transposed-conv MMAs, peer: relays "my half of the stage landed" to the leader
+//   4-7 A-tile producers   8-11 / 12-15 SwiGLU groups of even / odd chunks   16-19 output warps (D2 + bias + residual -> y)
+// The output pass used to ride in the SwiGLU groups' gaps; the round-2 trace showed each group losing ~4.5 k clk per
+// tile to it (global round trips inside the group's instruction stream), which delayed D1_EMPTY / G_FULL and stalled
+// both MMA warps ~6 k clk per tile.  It now has its own warpgroup: the SwiGLU groups only ever wait on the tensor pipe.
 // Only the leader CTA (cluster rank 0) issues MMAs; tcgen05.commit ... .multicast::cluster signals both CTAs.
 // Barriers that feed the MMA warps (A_FULL, D1_EMPTY, G_FULL, D2_EMPTY, PW_FULL) live in the leader and collect one
 // arrival per warp of BOTH CTAs (remote arrive through mapa).  Verified stand-alone: profiles/cta2_selftest.cu.
@@ -29,9 +33,21 @@ struct Ffn2Geom {
   uint32_t off_a, off_g, off_w, off_tab, off_bar, smem_bytes;
 };
 constexpr int FFN2_NA = 3;             // A-tile slots: the tile being multiplied and two ahead
-constexpr int FFN2_THREADS = 512;
-#ifndef FFN2_FIN_N
-#define FFN2_FIN_N 4   // 16-column output-pass steps per call: one call per tile measured best (2.33 ms; 2: 2.48; 1: 2.54)
+constexpr int FFN2_THREADS = 640;
+// setmaxnreg budgets per warpgroup: loaders / MMA issuers, A producers, SwiGLU groups (x2), output warps.  setmaxnreg
+// only re-splits what the CTA was given at launch -- 640 threads x 96 registers -- so the five budgets must sum to
+// <= 5 * 96 = 480 (the 4096 registers of the SM that the launch did not allocate are out of reach; asking for more
+// parks the last warpgroup in its TRY_ALLOC loop forever).
+constexpr int FFN2_REGS_CTRL = 56, FFN2_REGS_PROD = 96, FFN2_REGS_SWIGLU = 128, FFN2_REGS_OUT = 72;
+static_assert(FFN2_REGS_CTRL + FFN2_REGS_PROD + 2 * FFN2_REGS_SWIGLU + FFN2_REGS_OUT <= 480, "register budget of the CTA");
+#ifndef FFN2_MERGED_FULL
+#define FFN2_MERGED_FULL 1   // 1: the peer's "my half landed" relay arrives on the leader's W*_FULL barrier itself (count 2), so the
+                             //    issuing lane polls ONE barrier per weight stage (a try_wait costs ~90 clk even when complete)
+#endif
+#ifdef TFL_NO_SETMAXNREG   // bisecting aid: every warp keeps its launch allocation
+#define FFN2_SETMAXNREG(dir, n) do { } while (0)
+#else
+#define FFN2_SETMAXNREG(dir, n) asm volatile("setmaxnreg." dir ".sync.aligned.u32 %0;" ::"n"(n))
 #endif
 
 inline bool ffn2_geometry(int C, int H, int KT, int G, Ffn2Geom* g) {
@@ -48,7 +64,7 @@ inline bool ffn2_geometry(int C, int H, int KT, int G, Ffn2Geom* g) {
   g->half_bytes = w1_full / 2;
   g->a_slot_bytes = (uint32_t)(C / 8) * g->AR * 16;
   g->g_buf_bytes = (uint32_t)(TC_HC / 8) * g->AR * 16;
-  if (g->a_slot_bytes < 2u * 128u * (16 * 4 + 16)) return false;    // output strips of both groups live in the A slot
+  if (g->a_slot_bytes < 128u * (16 * 4 + 16)) return false;         // the output warps' strips live in the A slot
   uint32_t off = 0;
   g->off_a = off; off += FFN2_NA * g->a_slot_bytes;
   g->off_g = off; off += 2 * g->g_buf_bytes;
@@ -149,13 +165,13 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return ok != 0;
 }
 // wait on a barrier other CTAs of the cluster arrive on (acquire at cluster scope); bounded like mbar_wait
-__device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity);
+__device__ __forceinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity);
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   if (mbar_try_wait_cluster(bar, parity)) return;
   mbar_wait_cluster_slow(bar, parity);
 }
-__device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   for (;;) {
 #pragma unroll 1
@@ -263,15 +279,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
     for (uint32_t i = threadIdx.x; i < 2 * g.g_buf_bytes / 4; i += blockDim.x) gz[i] = 0u;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(BAR(WA_FULL + i), 1); mbar_init(BAR(WA_EMPTY + i), 1); mbar_init(BAR(PWA_FULL + i), 1); }
-    for (int i = 0; i < 6; ++i) { mbar_init(BAR(WB_FULL + i), 1); mbar_init(BAR(WB_EMPTY + i), 1); mbar_init(BAR(PWB_FULL + i), 1); }
+    const uint32_t full_count = (FFN2_MERGED_FULL && rank == 0) ? 2 : 1;   // leader: own loader + the peer's relay
+    for (int i = 0; i < 8; ++i) { mbar_init(BAR(WA_FULL + i), full_count); mbar_init(BAR(WA_EMPTY + i), 1); mbar_init(BAR(PWA_FULL + i), 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(BAR(WB_FULL + i), full_count); mbar_init(BAR(WB_EMPTY + i), 1); mbar_init(BAR(PWB_FULL + i), 1); }
     for (int i = 0; i < NA; ++i) { mbar_init(BAR(A_FULL + i), 8); mbar_init(BAR(A_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(D1_FULL + i), 1); mbar_init(BAR(D1_EMPTY + i), 8);
       mbar_init(BAR(G_FULL + i), 8); mbar_init(BAR(G_EMPTY + i), 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 16); }
-    mbar_init(BAR(F_DONE), 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(D2_FULL + i), 1); mbar_init(BAR(D2_EMPTY + i), 8); }   // 4 output warps x 2 CTAs
+    mbar_init(BAR(F_DONE), 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -294,8 +311,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
   auto tile_of = [&](int it) { return ((long long)cl + (long long)it * n_cl) * 2 + (long long)rank; };
 
   const uint32_t ringA = sbase + g.off_w, ringB = ringA + (uint32_t)NSA * g.half_bytes;
+  // (each role branch starts with its own setmaxnreg: ptxas bounds a region by the setmaxnreg that dominates it, and
+  // only when the region makes no calls -- the bounded waits are force-inlined for that reason)
   if (warp == 0 || warp == 2) {
     // ===================== weight loaders: warp 0 the conv1d stages, warp 2 the transposed-conv stages (this CTA's half) ====
+    FFN2_SETMAXNREG("dec", FFN2_REGS_CTRL);
     const bool isA = warp == 0;
     const int per_chunk = isA ? n1 : KS, nslots = isA ? NSA : NSB;
     const int FULL = isA ? WA_FULL : WB_FULL, EMPTY = isA ? WA_EMPTY : WB_EMPTY;
@@ -318,10 +338,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
     }
   } else if (rank == 1 && (warp == 1 || warp == 3)) {
     // ===================== peer CTA: tell the leader that my half of a stage has landed (one relay per ring) ==========
+    FFN2_SETMAXNREG("dec", FFN2_REGS_CTRL);
     if (elect_one()) {
       const bool isA = warp == 1;
       const int total = Q * (isA ? n1 : KS), nslots = isA ? NSA : NSB;
-      const int FULL = isA ? WA_FULL : WB_FULL, PFULL = isA ? PWA_FULL : PWB_FULL;
+      const int FULL = isA ? WA_FULL : WB_FULL, PFULL = FFN2_MERGED_FULL ? FULL : (isA ? PWA_FULL : PWB_FULL);
       uint32_t slot = 0, ph = 0;
       _Pragma("unroll 1") for (int s = 0; s < total; ++s) {
         mbar_wait(BAR(FULL + slot), ph);
@@ -331,6 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers (leader CTA): warp 1 conv1d taps, warp 3 transposed conv =====================
+    FFN2_SETMAXNREG("dec", FFN2_REGS_CTRL);
     if (elect_one()) {
       const bool is_m1 = warp == 1;
       const uint32_t idesc1 = instr_desc(256, 2 * TC_HC), idesc2 = instr_desc(256, C);
@@ -367,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
               const long long t0 = mtr ? clock64() : 0;
               mbar_wait(BAR(WA_FULL + wslot), wph);
               const long long t1 = mtr ? clock64() : 0;
-              mbar_wait(BAR(PWA_FULL + wslot), wph);
+              if (!FFN2_MERGED_FULL) mbar_wait(BAR(PWA_FULL + wslot), wph);
               if (mtr) { acc_w += t1 - t0; acc_pw += clock64() - t1; }
               tc_fence_after();
               const uint32_t wb = w16 + wslot * stage16;
@@ -400,7 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
           const uint32_t gb = g16 + b * gbuf16;
           for (int s = 0; s < KS; ++s) {
             mbar_wait(BAR(WB_FULL + wslot), wph);
-            mbar_wait(BAR(PWB_FULL + wslot), wph);
+            if (!FFN2_MERGED_FULL) mbar_wait(BAR(PWB_FULL + wslot), wph);
             tc_fence_after();
             const uint32_t wb = w16 + wslot * stage16;
             for (int tl = 0; tl < TPS; ++tl) {
@@ -421,6 +443,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
     }
   } else if (warp < 8) {
     // ===================== A producers: x -> RMSGroupNorm -> bf16 chunk-major A tile, two tiles ahead =====================
+    // (producers keep the launch allocation of 96 registers)
     const int tp = threadIdx.x - 128;  // 0..127
     const int G = g.G, D = C / G;
     const float rs = rsqrtf((float)D);
@@ -478,32 +501,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
       }
       if (++slot == (uint32_t)NA) { slot = 0; ph ^= 1; }
     }
-  } else {
+  } else if (warp < 16) {
     // ===================== SwiGLU groups: group b takes the chunks with running index q = b (mod 2) =====================
+    FFN2_SETMAXNREG("inc", FFN2_REGS_SWIGLU);
     const int b = (warp - 8) >> 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;       // tile row
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     uint8_t* gt = smem + g.off_g + (size_t)b * g.g_buf_bytes;
-    constexpr uint32_t FPITCH = 16 * 4 + 16;               // output strip row: 16 fp32 + 16 B
-    const int frow = lane >> 2, fcol = (lane & 3) * 4;      // coalesced phase: 4 lanes per row, 8 rows per instruction
     unsigned long long* const etr = warp == 8 ? tr : nullptr;
     auto arrive_leader = [&](int bar_index) {                // one arrival per warp, on the leader's barrier
       __syncwarp();
       if (lane == 0) { if (rank == 0) mbar_arrive(BAR(bar_index)); else mbar_arrive_cluster(BAR(bar_index), 0); }
     };
-    // Output pass of a finished tile: transposed-conv accumulator + bias + residual -> y, in steps of 16 columns.
-    // Group b owns the columns [b * C/2, (b + 1) * C/2) and spreads its C / 32 steps over its chunks of the NEXT tile
-    // (D2 is double-buffered over tiles), so the pass rides in the slack between two SwiGLU chunks instead of holding
-    // the group for a whole tile's worth of global round trips.  TMEM hands every thread one ROW; each warp passes its
-    // 32 rows through a padded strip in shared memory (the finished tile's own A slot; the producers wait for F_DONE)
-    // and walks it with 4 lanes per row (64 contiguous bytes): the read-modify-write of x / y touches 8 lines per
-    // instruction instead of 32.  The residual of the next step is requested before this step's stores.
-    const int fin_steps = C / 32;                            // steps of this group per tile
-    auto finish_steps = [&](int it, int k0, int n) {
+    _Pragma("unroll 1") for (int q = b; q < Q; q += 2) {
+      const int c = q % NC;
+      const uint32_t use = (uint32_t)(q >> 1) & 1;
+      mbar_wait(BAR(D1_FULL + b), use);
+      tc_fence_after();
+      trace_event(etr, 3, q);
+      uint32_t packed[TC_HC / 2];
+      const float* bv = tab_b1 + c * TC_HC;
+      const float* bg = tab_b1 + H + c * TC_HC;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t rv[32], rg[32];
+        tmem_ld32(lane_addr + b * 128 + half * 32, rv);
+        tmem_ld32(lane_addr + b * 128 + TC_HC + half * 32, rg);
+        tc_wait_ld();
+        if (half == 1) {  // D1[b] fully read: hand it back before the math
+          tc_fence_before();
+          arrive_leader(D1_EMPTY + b);
+          trace_event(etr, 4, q);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          packed[half * 16 + (i >> 1)] = swiglu_pair_bf16(rv[i], rv[i + 1], rg[i], rg[i + 1],
+                                                          *reinterpret_cast<const float2*>(bv + half * 32 + i),
+                                                          *reinterpret_cast<const float2*>(bg + half * 32 + i));
+      }
+      trace_event(etr, 10, q);
+      mbar_wait(BAR(G_EMPTY + b), use ^ 1);    // the transposed-conv MMAs of chunk q - 2 are done with G[b]
+      trace_event(etr, 5, q);
+#pragma unroll
+      for (int ch = 0; ch < TC_HC / 8; ++ch)
+        *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
+            make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+      fence_proxy_async();
+      arrive_leader(G_FULL + b);
+      trace_event(etr, 6, q);
+    }
+  } else {
+    // ===================== output warps: transposed-conv accumulator + bias + residual -> y =====================
+    // One warp per TMEM lane quarter (32 rows of the tile), 16 columns per step.  TMEM hands every thread one ROW; the
+    // warp passes its 32 rows through a padded strip in shared memory (the finished tile's own A slot; the producers
+    // wait for F_DONE before they overwrite it) and walks it with 4 lanes per row (64 contiguous bytes): the
+    // read-modify-write of x / y touches 8 lines per instruction instead of 32.  The residual of the next step is
+    // requested before this step's stores, the first step's before the accumulator is complete.
+    FFN2_SETMAXNREG("dec", FFN2_REGS_OUT);
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    constexpr uint32_t FPITCH = 16 * 4 + 16;               // output strip row: 16 fp32 + 16 B
+    const int frow = lane >> 2, fcol = (lane & 3) * 4;      // coalesced phase: 4 lanes per row, 8 rows per instruction
+    const int n_steps = C / 16;
+    unsigned long long* const otr = warp == 16 ? tr : nullptr;
+    _Pragma("unroll 1") for (int it = 0; it < n_iter; ++it) {
       const long long tile = tile_of(it);
-      const int d2b = it & 1;
-      const int col0 = b * (C / 2);
+      const uint32_t d2b = it & 1;
       int pos[4];
       _Pragma("unroll") for (int i = 0; i < 4; ++i) {
         const int mm = quarter * 32 + 8 * i + frow;
@@ -516,108 +580,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
       }
       auto fetch = [&](float4 (&xv)[4], int k) {
         _Pragma("unroll") for (int i = 0; i < 4; ++i)
-          xv[i] = pos[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)pos[i] * C + col0 + k * 16 + fcol))
+          xv[i] = pos[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)pos[i] * C + k * 16 + fcol))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      uint8_t* strip = smem + g.off_a + (size_t)((uint32_t)it % NA) * g.a_slot_bytes + (size_t)b * (128 * FPITCH) +
-                       (size_t)(quarter * 32) * FPITCH;
+      uint8_t* strip = smem + g.off_a + (size_t)((uint32_t)it % NA) * g.a_slot_bytes + (size_t)(quarter * 32) * FPITCH;
       float4 xa[4], xb[4];
-      fetch(xa, k0);
-      if (k0 == 0) {
-        mbar_wait(BAR(D2_FULL + d2b), (uint32_t)((it >> 1) & 1));
-        trace_event(etr, 13, it);
-      }
+      fetch(xa, 0);
+      mbar_wait(BAR(D2_FULL + d2b), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      _Pragma("unroll 1") for (int k = k0; k < k0 + n; ++k) {
+      trace_event(otr, 13, it);
+      _Pragma("unroll 1") for (int k = 0; k < n_steps; ++k) {
         {
           uint32_t r[16];
-          tmem_ld16(lane_addr + d2_col0 + d2b * C + col0 + k * 16, r);
+          tmem_ld16(lane_addr + d2_col0 + d2b * C + k * 16, r);
           tc_wait_ld();
           _Pragma("unroll") for (int e = 0; e < 4; ++e)
             *reinterpret_cast<uint4*>(strip + (size_t)lane * FPITCH + e * 16) = make_uint4(r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
         }
-        if (k == fin_steps - 1) {                            // this group's half of D2 fully read
+        if (k == n_steps - 1) {                              // D2[d2b] fully read by this warp
           tc_fence_before();
-          arrive_leader(D2_EMPTY + d2b);
+          __syncwarp();
+          if (lane == 0) { if (rank == 0) mbar_arrive(BAR(D2_EMPTY + d2b)); else mbar_arrive_cluster(BAR(D2_EMPTY + d2b), 0); }
         }
         __syncwarp();
-        if (k + 1 < k0 + n) fetch(xb, k + 1);
-        const float4 bb = *reinterpret_cast<const float4*>(tab_b2 + col0 + k * 16 + fcol);
+        if (k + 1 < n_steps) fetch(xb, k + 1);
+        const float4 bb = *reinterpret_cast<const float4*>(tab_b2 + k * 16 + fcol);
         _Pragma("unroll") for (int i = 0; i < 4; ++i) {
           const float4 d = *reinterpret_cast<const float4*>(strip + (size_t)(8 * i + frow) * FPITCH + fcol * 4);
           if (pos[i] >= 0) {
             float4 o = xa[i];
             o.x += d.x + bb.x; o.y += d.y + bb.y; o.z += d.z + bb.z; o.w += d.w + bb.w;
-            *reinterpret_cast<float4*>(p.y + (long long)pos[i] * C + col0 + k * 16 + fcol) = o;
+            *reinterpret_cast<float4*>(p.y + (long long)pos[i] * C + k * 16 + fcol) = o;
           }
         }
         __syncwarp();
         _Pragma("unroll") for (int i = 0; i < 4; ++i) xa[i] = xb[i];
       }
-      if (k0 + n == fin_steps) {
-        trace_event(etr, 14, it);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(F_DONE));             // this group's strips (the tile's A slot) may be rewritten
-      }
-    };
-    int fin_it = -1, fin_k = 0;                              // tile whose output pass is in progress, steps done
-    _Pragma("unroll 1") for (int q = b; q < Q + 2; q += 2) {
-      const int c = q % NC;
-      const uint32_t use = (uint32_t)(q >> 1) & 1;
-      if (q < Q) {
-        mbar_wait(BAR(D1_FULL + b), use);
-        tc_fence_after();
-        trace_event(etr, 3, q);
-        uint32_t packed[TC_HC / 2];
-        const float* bv = tab_b1 + c * TC_HC;
-        const float* bg = tab_b1 + H + c * TC_HC;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t rv[32], rg[32];
-          tmem_ld32(lane_addr + b * 128 + half * 32, rv);
-          tmem_ld32(lane_addr + b * 128 + TC_HC + half * 32, rg);
-          tc_wait_ld();
-          if (half == 1) {  // D1[b] fully read: hand it back before the math
-            tc_fence_before();
-            arrive_leader(D1_EMPTY + b);
-            trace_event(etr, 4, q);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            packed[half * 16 + (i >> 1)] = swiglu_pair_bf16(rv[i], rv[i + 1], rg[i], rg[i + 1],
-                                                            *reinterpret_cast<const float2*>(bv + half * 32 + i),
-                                                            *reinterpret_cast<const float2*>(bg + half * 32 + i));
-        }
-        trace_event(etr, 10, q);
-        mbar_wait(BAR(G_EMPTY + b), use ^ 1);    // the transposed-conv MMAs of chunk q - 2 are done with G[b]
-        trace_event(etr, 5, q);
-#pragma unroll
-        for (int ch = 0; ch < TC_HC / 8; ++ch)
-          *reinterpret_cast<uint4*>(gt + ((size_t)ch * AR + m) * 16) =
-              make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-        fence_proxy_async();
-        arrive_leader(G_FULL + b);
-        trace_event(etr, 6, q);
-      }
-      // a slice of the output pass of the previous tile (all that is left at this group's last chunk of a tile)
-      const int prev = q / NC - 1;
-      if (prev != fin_it) { fin_it = prev; fin_k = 0; }
-      if (fin_it >= 0 && fin_it < n_iter && fin_k < fin_steps) {
-        const int left = fin_steps - fin_k;
-        const bool last_chance = q >= Q || c + 2 >= NC;
-        // the single-purpose resource comes first: when this group's next accumulator is already waiting, read it back
-        // (the conv1d MMAs two chunks on need the buffer) and leave the output pass for a later gap
-        bool busy = false;
-        if (!last_chance && q + 2 < Q) {
-          int rdy = lane == 0 ? (int)mbar_try_wait(BAR(D1_FULL + b), (uint32_t)((q + 2) >> 1) & 1) : 0;
-          busy = __shfl_sync(0xffffffffu, rdy, 0) != 0;
-        }
-        if (!busy) {
-          const int n = last_chance ? left : (left < FFN2_FIN_N ? left : FFN2_FIN_N);
-          finish_steps(fin_it, fin_k, n);
-          fin_k += n;
-        }
-      }
+      trace_event(otr, 14, it);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(F_DONE));               // this warp's strip (the tile's A slot) may be rewritten
     }
   }
   tc_fence_before();

@@ -65,7 +65,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ unsigned int g_wait_timeout[5] = {0, 0, 0, 0, 0};
 __device__ unsigned int* g_timeout_host = nullptr;
 constexpr long long WAIT_LIMIT_CLOCKS = 4000000000LL;         // ~2 s at 1.9 GHz; legitimate waits are < 1 ms
-__device__ __noinline__ void wait_expired(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void wait_expired(uint32_t bar, uint32_t parity) {
   if (atomicCAS(&g_wait_timeout[0], 0u, 1u) == 0u) {
     g_wait_timeout[1] = blockIdx.x; g_wait_timeout[2] = threadIdx.x; g_wait_timeout[3] = bar; g_wait_timeout[4] = parity;
     unsigned int* h = g_timeout_host;
@@ -78,7 +78,7 @@ __device__ __noinline__ void wait_expired(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   for (;;) {
 #pragma unroll 1

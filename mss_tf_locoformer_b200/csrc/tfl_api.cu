@@ -225,6 +225,7 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
         TFL_CHECK(tc_pack_ffn(w1, b1, w2, b2, (char*)packed + f.tc, C, H, K, st) == 0, "tc_pack_ffn failed");
         if (f.tc2_ok) TFL_CHECK(tc_pack_ffn2(w1, w2, (char*)packed + f.tc2, C, H, K, st) == 0, "tc_pack_ffn2 failed");
       }
+      const float* attn_gamma_raw = w[i];
       copy(w[i++], p.attn_gamma, C);
       if (c.rope) copy(w[i++], p.rope, pl->head_dim / 2);
       const float* wqkv_raw = w[i++];
@@ -232,9 +233,10 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
       permute(wqkv_raw, dst(p.wqkv), 1, 1, C, 3 * A, 0, 0, 1, C, 0, -1, st);  // [3A, C] -> [C][3A]
       permute(wo_raw, dst(p.wo), 1, 1, A, C, 0, 0, 1, A, 0, -1, st);          // [C, A] -> [A][C]
       if (attn_tc_supported(C, c.n_heads, pl->head_dim))
-        tc_pack_qkv_kernel<<<296, 256, 0, st>>>(wqkv_raw, wo_raw, (__nv_bfloat16*)(base + p.tc_qkv),
+        tc_pack_qkv_kernel<<<296, 256, 0, st>>>(wqkv_raw, wo_raw, attn_gamma_raw, (__nv_bfloat16*)(base + p.tc_qkv),
                                                 (__nv_bfloat16*)(base + p.tc_wo), C, A, c.n_heads, pl->head_dim,
-                                                (pl->head_dim + 15) / 16 * 16);
+                                                (pl->head_dim + 15) / 16 * 16,
+                                                1.4426950408889634f / sqrtf((float)pl->head_dim));
     }
   if (c.enc_in_ch > 0) {
     // deconv.weight [C, 2S, 3, 3] -> [9][8][C] (outputs >= 2S stay zero from the memset)
@@ -536,8 +538,12 @@ int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, 
   double* part = (double*)(wsp + ws.gln_part);
   float* stats = (float*)(wsp + ws.gln_stats);
   const size_t smem = ((size_t)9 * 2 * C + C) * sizeof(float);
-  enc_conv_kernel<2><<<dim3(ws.gln_blocks, B), 256, smem, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
-                                                              (const float*)(base + pl->lay.enc_b), x, part);
+  if (C % 4 == 0 && 256 % (C / 4) == 0)
+    enc_conv_reg_kernel<2><<<dim3(ws.gln_blocks, B), 256, 0, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
+                                                                  (const float*)(base + pl->lay.enc_b), x, part);
+  else
+    enc_conv_kernel<2><<<dim3(ws.gln_blocks, B), 256, smem, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
+                                                                (const float*)(base + pl->lay.enc_b), x, part);
   TFL_LAUNCH_CHECK();
   gln_finalize_kernel<<<B, 256, 0, st>>>(part, ws.gln_blocks, (double)Tf * F * C, c.eps, stats);
   TFL_LAUNCH_CHECK();

@@ -25,12 +25,15 @@ names = {0: "m1_start", 1: "m1_ready", 2: "m1_issued", 3: "epi_d1full", 4: "epi_
 base = int(t[0, 6])
 print("chunk " + " ".join(f"{names[e]:>13s}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)))
 print("(last two columns: clocks the MMA warp spent waiting for weight stages in M1 / M2 of the chunk)")
-for c in range(6, 30):
-    print(f"{c:5d} " + " ".join(f"{int(t[e, c]) - base:13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)) + f" {int(t[11, c]):8d} {int(t[12, c]):8d}")
+def rel(v):
+    return int(v) - base if int(v) else -1
 
-print("epilogue group 0: output pass start (D2 full seen), end")
+
+print("(last three columns: clocks the MMA warp waited for weight stages in M1 / for the peer's half / for the A tile)")
+for c in range(6, 30):
+    print(f"{c:5d} " + " ".join(f"{rel(t[e, c]):13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)) +
+          f" {int(t[11, c]):8d} {int(t[12, c]):8d} {int(t[15, c]):8d}")
+
+print("output warp 16: output pass start (D2 full seen), end")
 for it in range(1, 6):
     print(it, int(t[13, it]) - base, int(t[14, it]) - base)
-print("produce(it): A_EMPTY seen tile 0, tile 0 written, A_EMPTY seen tile 1, tile 1 written")
-for it in range(2, 8):
-    print(it, *[int(t[13, 32 + 4 * it + k]) - base for k in range(4)])
