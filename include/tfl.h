@@ -121,6 +121,12 @@ int tfl_separator_forward(const tfl_plan* plan, const void* packed, const float*
 int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, int seg_index0,
                     int n_seg_total, float* track, int64_t n_track, int64_t track_origin, tfl_stream_t stream);
 
+/* evaluation/metrics.py:14-168 on the device.  est, tgt [rows, n] fp32 -> out5 [rows][5] double =
+ * {sum e, sum t, sum e^2, sum t^2, sum e*t}: SI-SDR, SDR and the file's "SAR" / "SIR" are closed forms of these sums
+ * (mss_tf_locoformer_b200/metrics.py).  scratch: >= rows * 64 * 5 doubles. */
+int tfl_pair_stats(const float* est, const float* tgt, int rows, int64_t n, double* out5, double* scratch,
+                   size_t scratch_bytes, tfl_stream_t stream);
+
 /* Every mbarrier wait in the tcgen05 kernels is bounded (~2 s).  A wait that expires is a pipeline protocol error: the
  * kernel records {1, block, thread, shared-memory address of the barrier, parity} in a host-mapped record and traps, so
  * the launch fails loudly (cudaErrorLaunchFailed at the next synchronising call) and every later tfl_* entry point
@@ -142,8 +148,9 @@ int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan,
 /* Diagnostic: process-wide switches used for A/B measurements (not part of the reference-facing surface).
  *   TFL_OPT_ATTN_KERNEL  1 = attn_tc_kernel (P through shared memory), 2 = attn_tc2_kernel (P in TMEM; default)
  *   TFL_OPT_FFN_KERNEL   1 = ffn_tc_kernel (two tiles per CTA), 2 = ffn_tc2_kernel (cta_group::2, one tile per CTA of a
- *                        2-CTA cluster; default where the shape allows it) */
-enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_COUNT = 4 };
+ *                        2-CTA cluster; default where the shape allows it)
+ *   TFL_OPT_TRACE_BASE   first chunk / tile index the pipeline trace records (64 entries per event; default 0) */
+enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_TRACE_BASE = 2, TFL_OPT_COUNT = 4 };
 int tfl_debug_set_option(int key, int value);
 
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN

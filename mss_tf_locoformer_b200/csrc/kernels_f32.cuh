@@ -630,4 +630,42 @@ __global__ void __launch_bounds__(256) segment_ola_kernel(const float* __restric
   }
 }
 
+// --------------------------------------------------------------------------------------
+// Pair statistics for the evaluation metrics (evaluation/metrics.py:14-168): per row r of two
+// [rows, n] signals, out[r] = {sum e, sum t, sum e*e, sum t*t, sum e*t} in double.  Every metric of
+// that file (SI-SDR, SDR, "SAR", "SIR") is a closed form of these five sums, so a track never has
+// to leave the device to be scored.  Deterministic: fixed grid, block partials, ordered finish.
+// --------------------------------------------------------------------------------------
+constexpr int STATS_BLOCKS = 64;
+__global__ void __launch_bounds__(256) pair_stats_partial_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
+                                                                 long long n, double* __restrict__ partial /*[rows][blocks][5]*/) {
+  const int row = blockIdx.y;
+  const float* e = est + (size_t)row * n;
+  const float* t = tgt + (size_t)row * n;
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = (double)e[i], b = (double)t[i];
+    s[0] += a; s[1] += b; s[2] += a * a; s[3] += b * b; s[4] += a * b;
+  }
+  __shared__ double red[5][256];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) red[k][threadIdx.x] = s[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) partial[((size_t)row * gridDim.x + blockIdx.x) * 5 + threadIdx.x] = red[threadIdx.x][0];
+}
+__global__ void pair_stats_finish_kernel(const double* __restrict__ partial, int n_blocks, double* __restrict__ out /*[rows][5]*/) {
+  const int row = blockIdx.x, k = threadIdx.x;
+  if (k >= 5) return;
+  double s = 0.0;
+  for (int b = 0; b < n_blocks; ++b) s += partial[((size_t)row * n_blocks + b) * 5 + k];
+  out[(size_t)row * 5 + k] = s;
+}
+
 }  // namespace tfl

@@ -17,6 +17,7 @@
 //     Tensor-pipe order per hidden chunk c: M1[0](c) M1[1](c) M2[0](c-1) M2[1](c-1); the SwiGLU
 //     epilogue of chunk c overlaps M2(c-1) and M1(c+1).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -774,6 +775,8 @@ inline int tc_ffn2_dispatch(const tfl_plan* pl, const FfnTcParams& p, int C, int
 // y = x + ConvSwiGLU(RMSGroupNorm(x)); x and y must be distinct buffers.
 inline int tc_ffn(const tfl_plan* pl, const char* packed, int layer, int axis, int j, const float* x, float* y, int B,
                   int Tf, int F, cudaStream_t st) {
+  nvtxRangePushA("tfl::conv_swiglu_ffn[bf16]");
+  struct Pop { ~Pop() { nvtxRangePop(); } } nvtx_pop;
   TFL_CHECK(x != y, "tc_ffn needs distinct input and output buffers");
   const tfl_config& c = pl->cfg;
   const FfnPack& f = pl->lay.paths[(size_t)layer * 2 + axis].ffn[j];

@@ -44,6 +44,18 @@ static_assert(FFN2_REGS_CTRL + FFN2_REGS_PROD + 2 * FFN2_REGS_SWIGLU + FFN2_REGS
 #define FFN2_MERGED_FULL 1   // 1: the peer's "my half landed" relay arrives on the leader's W*_FULL barrier itself (count 2), so the
                              //    issuing lane polls ONE barrier per weight stage (a try_wait costs ~90 clk even when complete)
 #endif
+#ifndef FFN2_CTA_WAIT
+#define FFN2_CTA_WAIT 1      // 1: the MMA lanes observe A_FULL / D1_EMPTY / G_FULL / D2_EMPTY with a CTA-scope wait.  The barriers
+                             //    carry no memory the waiting lane reads: the tiles are read by each SM's own tensor core (ordered by
+                             //    the writers' fence.proxy.async before their release arrive) and TMEM hand-offs are ordered by
+                             //    tcgen05.fence.  A cluster-scope acquire costs ~0.5 k clk per wait (it invalidates L1): the
+                             //    steady-state trace (r02, batch 8) had the conv1d lane spend 0.5-1.2 k clk of every 4.3 k clk chunk there.
+#endif
+#if FFN2_CTA_WAIT
+#define FFN2_WAIT(bar, parity) mbar_wait(bar, parity)
+#else
+#define FFN2_WAIT(bar, parity) mbar_wait_cluster(bar, parity)
+#endif
 #ifdef TFL_NO_SETMAXNREG   // bisecting aid: every warp keeps its launch allocation
 #define FFN2_SETMAXNREG(dir, n) do { } while (0)
 #else
@@ -139,12 +151,25 @@ __device__ __forceinline__ uint32_t n_clusters_x() { uint32_t r; asm volatile("m
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  What the arrival publishes is
+// data of the ARRIVING CTA only -- its own A / G tile (read by its own SM's tensor core; made visible to the async proxy
+// by the fence.proxy.async before this call) or a finished TMEM read -- so the release is CTA scope: a cluster-scope
+// release flushes L1 and costs ~1 k clk, which every warp of the peer CTA paid on each hand-off (FFN2_CTA_RELEASE = 0).
+#ifndef FFN2_CTA_RELEASE
+#define FFN2_CTA_RELEASE 1
+#endif
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+#if FFN2_CTA_RELEASE
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cta.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+#else
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+#endif
 }
 // bookkeeping arrivals that order no data of the arriving thread (ring-slot releases by a warp that merely stepped
 // over the stage, "my half landed" relays: the data was written by the async proxy and is read by the tensor core of
@@ -377,10 +402,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
           trace_event(mtr, 0, q);
           if (c == 0) {
             const long long ta = mtr ? clock64() : 0;
-            mbar_wait_cluster(BAR(A_FULL + aslot), aph);
-            if (mtr != nullptr && q < 64) mtr[15 * 64 + q] = (unsigned long long)(clock64() - ta);   // waited for the A tiles
+            FFN2_WAIT(BAR(A_FULL + aslot), aph);
+            if (mtr != nullptr && q - g_trace_base >= 0 && q - g_trace_base < 64) mtr[15 * 64 + q - g_trace_base] = (unsigned long long)(clock64() - ta);   // waited for the A tiles
           }
-          mbar_wait_cluster(BAR(D1_EMPTY + b), use ^ 1);
+          FFN2_WAIT(BAR(D1_EMPTY + b), use ^ 1);
           tc_fence_after();
           trace_event(mtr, 1, q);
           const uint32_t ab0 = a16 + aslot * aslot16;
@@ -401,7 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
           mma2_commit(BAR(D1_FULL + b));
           if (c == NC - 1) mma2_commit(BAR(A_EMPTY + aslot));
           trace_event(mtr, 2, q);
-          if (mtr != nullptr && q < 64) { mtr[11 * 64 + q] = (unsigned long long)acc_w; mtr[12 * 64 + q] = (unsigned long long)acc_pw; }
+          if (mtr != nullptr && q - g_trace_base >= 0 && q - g_trace_base < 64) { mtr[11 * 64 + q - g_trace_base] = (unsigned long long)acc_w; mtr[12 * 64 + q - g_trace_base] = (unsigned long long)acc_pw; }
           acc_w = acc_pw = 0;
           if (++c == NC) {
             c = 0;
@@ -414,9 +439,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
         _Pragma("unroll 1") for (int q = 0; q < Q; ++q) {
           const uint32_t b = q & 1, use = (uint32_t)(q >> 1) & 1;
           trace_event(mtr, 7, q);
-          mbar_wait_cluster(BAR(G_FULL + b), use);
+          FFN2_WAIT(BAR(G_FULL + b), use);
           const uint32_t d2b = it2 & 1;                     // D2 is double-buffered over tiles: the output pass of tile it2 - 2
-          if (cc == 0) mbar_wait_cluster(BAR(D2_EMPTY + d2b), (uint32_t)(((it2 >> 1) & 1) ^ 1));
+          if (cc == 0) FFN2_WAIT(BAR(D2_EMPTY + d2b), (uint32_t)(((it2 >> 1) & 1) ^ 1));
           tc_fence_after();
           trace_event(mtr, 8, q);
           const uint32_t gb = g16 + b * gbuf16;

@@ -101,8 +101,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Optional event trace (diagnostic): when tfl_debug_set_trace() has installed a buffer, block 0 of the traced kernels
 // stores clock64() stamps at [event * 64 + index].
 __device__ unsigned long long* g_trace = nullptr;
+__device__ int g_trace_base = 0;       // first chunk / tile index recorded (tfl_debug_set_option(TFL_OPT_TRACE_BASE, n))
 __device__ __forceinline__ void trace_event(unsigned long long* tr, int event, int index) {
-  if (tr != nullptr && index >= 0 && index < 64) tr[event * 64 + index] = (unsigned long long)clock64();
+  if (tr == nullptr) return;
+  index -= g_trace_base;
+  if (index >= 0 && index < 64) tr[event * 64 + index] = (unsigned long long)clock64();
 }
 
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

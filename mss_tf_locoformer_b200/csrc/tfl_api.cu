@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 
 #include "common.cuh"
 #include "kernels_f32.cuh"
@@ -60,6 +61,10 @@ void set_error(const char* fmt, ...) {
 }
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+struct NvtxRange {   // one range per stage / sub-block (nsys and ncu --nvtx group the launches under these names)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 
 // ---- generic strided-permute copy used by the weight packer ---------------------------
@@ -325,6 +330,7 @@ struct Dims { int B, Tf, F; };
 
 static int ffn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, int j, float* x, Dims d,
                    const Workspace& ws, char* wsp, cudaStream_t st) {
+  NvtxRange nvtx_range("tfl::conv_swiglu_ffn[fp32]");
   const tfl_config& c = pl->cfg;
   const FfnPack& f = pl->lay.paths[(size_t)layer * 2 + axis].ffn[j];
   const int C = c.emb_dim, K = c.conv_kernel, H = f.hidden;
@@ -345,6 +351,7 @@ static int ffn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, 
 
 static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
                     const Workspace& ws, char* wsp, cudaStream_t st) {
+  NvtxRange nvtx_range("tfl::rope_attn[fp32]");
   const tfl_config& c = pl->cfg;
   const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
   const int C = c.emb_dim, A = c.attention_dim, hd = pl->head_dim, heads = c.n_heads;
@@ -377,6 +384,7 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
 //   proj_tc  head merge projection + residual, in place on x
 static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
                      const Workspace& ws, char* wsp, cudaStream_t st) {
+  NvtxRange nvtx_range("tfl::rope_attn[bf16]");
   const tfl_config& c = pl->cfg;
   const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
   const int C = c.emb_dim, hd = pl->head_dim, heads = c.n_heads;
@@ -482,6 +490,7 @@ static int path_forward(const tfl_plan* pl, const char* packed, int layer, int a
 
 static int blocks_forward(const tfl_plan* pl, const char* packed, float* x, Dims d, const Workspace& ws, char* wsp,
                           int precision, cudaStream_t st) {
+  NvtxRange nvtx_range("tfl::blocks");
   float* cur = x;
   float* alt = (float*)(wsp + ws.tc);
   for (int layer = 0; layer < pl->cfg.n_layers; ++layer) {
@@ -509,6 +518,7 @@ size_t tfl_workspace_bytes(const tfl_plan* pl, int B, int Tf, int F, int precisi
 }
 
 int tfl_stft(const tfl_plan* pl, const void* packed, const float* audio, int B, int T, float* spec, tfl_stream_t stream) {
+  NvtxRange nvtx_range("tfl::stft");
   TFL_CHECK(pl && packed && audio && spec, "null argument");
   const tfl_config& c = pl->cfg;
   TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
@@ -526,6 +536,7 @@ int tfl_stft(const tfl_plan* pl, const void* packed, const float* audio, int B, 
 
 int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, int B, int Tf, int F, float* x,
                      void* workspace, size_t ws_bytes, tfl_stream_t stream) {
+  NvtxRange nvtx_range("tfl::enc_conv_gln");
   if (check_common(pl, packed, B, Tf, F, 0)) return -1;
   TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv encoder");
   const Workspace ws = plan_workspace(pl, B, Tf, F, 0);  // only the precision-independent prefix is used here
@@ -614,6 +625,7 @@ int tfl_rope_attn(const tfl_plan* pl, const void* packed, int layer, int axis, f
 
 int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, int Tf, int F, float* est,
                  tfl_stream_t stream) {
+  NvtxRange nvtx_range("tfl::dec_conv");
   if (check_common(pl, packed, B, Tf, F, 0)) return -1;
   TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv decoder");
   const int C = pl->cfg.emb_dim;
@@ -632,6 +644,7 @@ int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, 
 
 int tfl_istft_ola(const tfl_plan* pl, const void* packed, const float* est, int B, int Tf, int T, float* audio,
                   tfl_stream_t stream) {
+  NvtxRange nvtx_range("tfl::istft_ola");
   TFL_CHECK(pl && packed && est && audio, "null argument");
   const tfl_config& c = pl->cfg;
   TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
@@ -671,6 +684,7 @@ int tfl_separator_forward(const tfl_plan* pl, const void* packed, const float* s
 
 int tfl_forward(const tfl_plan* pl, const void* packed, const float* mixture, int B, int T, float* audio,
                 float* est_spec, void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
+  NvtxRange nvtx_range("tfl::forward");
   TFL_CHECK(pl && packed && mixture, "null argument");
   const tfl_config& c = pl->cfg;
   TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
@@ -726,9 +740,22 @@ int tfl_bs_band_decode(const float* x, const float* spec, int B, int M, int T, i
   return 0;
 }
 
+int tfl_pair_stats(const float* est, const float* tgt, int rows, int64_t n, double* out5, double* scratch,
+                   size_t scratch_bytes, tfl_stream_t stream) {
+  TFL_CHECK(est && tgt && out5 && scratch, "null argument");
+  TFL_CHECK(rows >= 1 && n >= 1, "empty input");
+  TFL_CHECK(scratch_bytes >= (size_t)rows * STATS_BLOCKS * 5 * sizeof(double), "scratch too small");
+  pair_stats_partial_kernel<<<dim3(STATS_BLOCKS, rows), 256, 0, (cudaStream_t)stream>>>(est, tgt, (long long)n, scratch);
+  TFL_LAUNCH_CHECK();
+  pair_stats_finish_kernel<<<rows, 32, 0, (cudaStream_t)stream>>>(scratch, STATS_BLOCKS, out5);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
 int tfl_debug_set_option(int key, int value) {
   TFL_CHECK(key >= 0 && key < TFL_OPT_COUNT, "unknown option %d", key);
   g_options[key].store(value, std::memory_order_relaxed);
+  if (key == TFL_OPT_TRACE_BASE) TFL_CUDA(cudaMemcpyToSymbol(tc::g_trace_base, &value, sizeof(int)));
   return 0;
 }
 

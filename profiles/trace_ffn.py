@@ -8,13 +8,15 @@ from mss_tf_locoformer_b200 import _lib
 cfg = dict(VARIANT_D)
 model = make_state_dict(cfg).cuda()
 eng = model._ready()
-B = 2
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+BASE = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # first chunk recorded (steady state: e.g. 300)
 Tf, F = 1 + SEG // cfg["hop_length"], cfg["n_fft"] // 2 + 1
 x = torch.randn(B, Tf, F, cfg["emb_dim"], device="cuda")
 for _ in range(2):
     eng.ffn_(0, 0, 0, x, 1)
 buf = torch.zeros(16 * 64, dtype=torch.int64, device="cuda")
 lib = _lib.load()
+lib.tfl_debug_set_option(2, BASE)
 lib.tfl_debug_set_trace(buf.data_ptr())
 eng.ffn_(0, 0, 0, x, 1)
 torch.cuda.synchronize()
@@ -30,10 +32,10 @@ def rel(v):
 
 
 print("(last three columns: clocks the MMA warp waited for weight stages in M1 / for the peer's half / for the A tile)")
-for c in range(6, 30):
-    print(f"{c:5d} " + " ".join(f"{rel(t[e, c]):13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)) +
+for c in range(6, 40):
+    print(f"{c + BASE:5d} " + " ".join(f"{rel(t[e, c]):13d}" for e in (0, 1, 2, 3, 4, 10, 5, 6, 7, 8, 9)) +
           f" {int(t[11, c]):8d} {int(t[12, c]):8d} {int(t[15, c]):8d}")
 
 print("output warp 16: output pass start (D2 full seen), end")
-for it in range(1, 6):
-    print(it, int(t[13, it]) - base, int(t[14, it]) - base)
+for it in range(1, 8):
+    print(it + BASE, int(t[13, it]) - base, int(t[14, it]) - base)

@@ -316,3 +316,69 @@ def test_full_track_two_gpus_nccl_matches_one_gpu(pkg):
             assert torch.allclose(res[r][k], one[k].cpu(), atol=1e-6, rtol=0), (r, k)
     for k in one:
         assert torch.equal(res[0][k], res[1][k])
+
+
+def test_device_metrics_match_reference_numpy(pkg):
+    """evaluation/metrics.py on the device (tfl_pair_stats) against the reference's numpy arithmetic."""
+    import numpy as np
+    from mss_tf_locoformer_b200 import metrics
+    g = torch.Generator().manual_seed(3)
+    t = torch.randn(2, 100001, generator=g)
+    e = 0.7 * t + 0.2 * torch.randn(2, 100001, generator=g) + 0.01
+    en, tn, eps = e.double().numpy().ravel(), t.double().numpy().ravel(), 1e-8
+    e0, t0 = en - en.mean(), tn - tn.mean()
+    sc = np.dot(e0, t0) / (np.dot(t0, t0) + eps)
+    want_si = 10 * np.log10((np.dot(sc * t0, sc * t0) + eps) / (np.dot(e0 - sc * t0, e0 - sc * t0) + eps))
+    want_sdr = 10 * np.log10((np.dot(tn, tn) + eps) / (np.dot(en - tn, en - tn) + eps))
+    sc2 = np.dot(en, tn) / (np.dot(tn, tn) + eps)
+    want_sar = 10 * np.log10((np.dot(sc2 * tn, sc2 * tn) + eps) / (np.dot(en - sc2 * tn, en - sc2 * tn) + eps))
+    got = metrics.compute_all_metrics(e.cuda(), t.cuda())
+    assert abs(got["si_sdr"] - want_si) < 1e-4 and abs(got["sdr"] - want_sdr) < 1e-4
+    assert abs(got["sar"] - want_sar) < 1e-4 and got["sir"] == got["sar"]
+    res = metrics.evaluate_source_separation({"vocals": e[0].cuda(), "bass": e[1].cuda()}, {"vocals": t[0].cuda(), "bass": t[1].cuda()})
+    assert set(res) == {"vocals", "bass", "average"} and "avg_si_sdr" in res["average"]
+
+
+def test_cli_end_to_end(pkg, tmp_path):
+    """the inference CLI (checkpoint + YAML -> wav files) against the oracle run through the same stitch."""
+    import os
+    import yaml
+    from mss_tf_locoformer_b200 import separate as cli
+    cfg, sd, arr = load_golden("mss_hop2_macaron")
+    ckpt = os.path.join(tmp_path, "model.pt")
+    torch.save({"model_state_dict": sd, "epoch": 3}, ckpt)           # utils/common.py:46-74 wrapper
+    ycfg = os.path.join(tmp_path, "cfg.yaml")
+    with open(ycfg, "w") as f:
+        yaml.safe_dump({"model": cfg, "training": {"lr": 1e-3}}, f)
+    sr = 8000
+    stereo = torch.stack([_mixture(9000, 1, seed=1)[0], _mixture(9000, 1, seed=2)[0]])
+    wav = os.path.join(tmp_path, "song.wav")
+    cli.save_audio(stereo, wav, sample_rate=sr, normalize=False)
+    out_dir = os.path.join(tmp_path, "out")
+    cli.main(["--input", wav, "--checkpoint", ckpt, "--config", ycfg, "--output_dir", out_dir, "--sample_rate", str(sr),
+              "--segment", str(1024 / sr), "--batch", "3", "--precision", "fp32"])
+    mono = stereo.mean(0)
+    want = oracle.separate_track(lambda x: oracle.mss_forward(sd, cfg, x), mono, 1024, batch=2)
+    for k in want:
+        got, got_sr = cli.load_audio(os.path.join(out_dir, f"song_{k}.wav"), sample_rate=sr)
+        assert got_sr == sr and got.shape == (2, 9000) and torch.equal(got[0], got[1])
+        ref = want[k] / want[k].abs().max()                          # save_audio(normalize=True)
+        _check(got[0], ref, maxabs=2e-4, what=f"cli/{k}")
+
+
+def test_espnet_adapter_forward(pkg):
+    """the ESPnet AbsSeparator surface (list of num_spk complex [B, T, F], ilens passthrough, OrderedDict)."""
+    from collections import OrderedDict
+    from mss_tf_locoformer_b200.espnet_separator import TFLocoformerSeparator as EspnetSeparator
+    cfg, sd, arr = load_golden("sep_rope_k8")
+    model = EspnetSeparator(arr["spec_in"].shape[-1], **cfg)
+    model.load_state_dict(pkg.strip_prefix({"separator." + k: v for k, v in sd.items()}), strict=True)
+    model = model.cuda().eval()
+    ilens = torch.tensor([arr["spec_in"].shape[1]] * arr["spec_in"].shape[0])
+    with torch.no_grad():
+        outs, ol, extra = model(arr["spec_in"].cuda(), ilens)
+        outs4, _, _ = model(arr["spec_in"].cuda().unsqueeze(2), ilens)          # ESPnet's [B, T, C = 1, F]
+    assert isinstance(extra, OrderedDict) and len(extra) == 0 and ol is ilens and len(outs) == model.num_spk
+    for s, o in enumerate(outs):
+        _check(o, arr["spec_out"][:, s], maxabs=2e-4, what=f"espnet/spk{s}")
+        assert torch.equal(o, outs4[s])
