@@ -421,6 +421,126 @@ __global__ void __launch_bounds__(256) attn_tail_rows_kernel(AttnTcParams p, int
   }
 }
 
+// Tail rows on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32): the CUDA-core kernel above
+// is bound by its instruction count on the time axis (3 tail rows x 4 heads x 8200 sequences: ~10 k warp instructions
+// per (sequence, head) for the scores, the bf16 -> fp32 conversions and the P.V FMAs; ncu r02: 0.47 ms per call against
+// 0.17 ms of K / V traffic).  Here one warp owns a (sequence, head): the <= 8 tail rows are rows 0..7 of an M = 16 tile,
+// keys are walked 16 at a time with an online softmax (flash style), ~60 instructions per 16 keys for ALL rows.
+//   S  = Q K^T : A = Q rows (fragments straight from the q image: 4-byte loads), B = K rows (4-byte loads, one 128-byte
+//                line per warp load)
+//   O += P V   : A = P (the S accumulator fragments re-packed as bf16: C layout of two n-tiles == A layout of one k-step),
+//                B = V via ldmatrix.trans from a 16-key block staged in shared memory (V is stored dims-contiguous).
+// Same images, same exp2 domain (q carries log2(e) / sqrt(hd)), P rounded to bf16 as in attn_tc2_kernel.
+template <int KS>   // head_dim padded to 16 * KS
+__global__ void __launch_bounds__(256) attn_tail_mma_kernel(AttnTcParams p, int row0) {
+  constexpr int HDP = 16 * KS, NT = 2 * KS;                  // NT = 8-wide n-tiles of the head dimension
+  constexpr int VPITCH = HDP * 2 + 16;                       // bytes per staged V row (padded: conflict-free ldmatrix)
+  __shared__ __align__(16) uint8_t vstage[8][16 * VPITCH];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tail = p.L - row0, NTL = p.NTL, OC = HDP / 8;
+  const long long total = (long long)p.nseq * p.heads;
+  const size_t plane = (size_t)p.nseq * p.heads * NTL * HDP * 128;
+  uint8_t* vs = vstage[wib];
+  const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(vs);
+  for (long long sh = (long long)blockIdx.x * 8 + wib; sh < total; sh += (long long)gridDim.x * 8) {
+    const __nv_bfloat16* qimg = p.qkv + (size_t)sh * NTL * HDP * 128;
+    const __nv_bfloat16* kimg = qimg + plane;
+    const __nv_bfloat16* vimg = qimg + 2 * plane;
+    // ---- Q fragments (rows g < n_tail; rows 8..15 of the tile stay zero) ----
+    uint32_t qa[KS][2];
+    {
+      const int row = row0 + g;
+      const bool valid = g < n_tail;
+      const __nv_bfloat16* qt = qimg + (size_t)(min(row, p.L - 1) >> 7) * HDP * 128 + (size_t)(min(row, p.L - 1) & 127) * 8 + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        qa[ks][0] = valid ? __ldg(reinterpret_cast<const uint32_t*>(qt + (size_t)(2 * ks) * 1024)) : 0u;
+        qa[ks][1] = valid ? __ldg(reinterpret_cast<const uint32_t*>(qt + (size_t)(2 * ks + 1) * 1024)) : 0u;
+      }
+    }
+    float o[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) o[j][0] = o[j][1] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int k0 = 0; k0 < p.L; k0 += 16) {
+      const size_t tile_off = (size_t)(k0 >> 7) * HDP * 128;
+      const int kr = k0 & 127;
+      // stage the 16 V rows of this block: OC chunks x 16 keys x 16 B, coalesced 16-byte pieces
+      for (int piece = lane; piece < OC * 16; piece += 32) {
+        const int c = piece >> 4, key = piece & 15;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(vimg + tile_off + ((size_t)c * 128 + kr + key) * 8));
+        *reinterpret_cast<uint4*>(vs + key * VPITCH + c * 16) = v;
+      }
+      // ---- S = Q K^T for keys k0 .. k0 + 15 (two n-tiles of 8 keys) ----
+      float sc[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+        const __nv_bfloat16* kt = kimg + tile_off + (size_t)(kr + 8 * n + g) * 8 + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(kt + (size_t)(2 * ks) * 1024));
+          const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(kt + (size_t)(2 * ks + 1) * 1024));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(sc[n][0]), "+f"(sc[n][1]), "+f"(sc[n][2]), "+f"(sc[n][3])
+                       : "r"(qa[ks][0]), "r"(0u), "r"(qa[ks][1]), "r"(0u), "r"(b0), "r"(b1));
+        }
+      }
+      // ---- online softmax on row g (this lane holds keys k0 + 8n + 2t, +1) ----
+      float s4[4] = {sc[0][0], sc[0][1], sc[1][0], sc[1][1]};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int key = k0 + 8 * (i >> 1) + 2 * t + (i & 1);
+        if (key >= p.L) s4[i] = -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run, mx);                  // finite: every block holds at least one key < L
+      const float alpha = fast_exp2(m_run - m_new);
+      float pr[4], psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { pr[i] = fast_exp2(s4[i] - m_new); psum += pr[i]; }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { o[j][0] *= alpha; o[j][1] *= alpha; }
+      const uint32_t pa0 = tc::pack_bf16(pr[0], pr[1]), pa2 = tc::pack_bf16(pr[2], pr[3]);   // A fragment rows g: k = 2t.., 2t + 8..
+      // ---- O += P V: B fragments through ldmatrix.trans (two n-tiles of dims per x4) ----
+      __syncwarp();
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        const int mtx = lane >> 3, r = lane & 7;             // matrix m: keys (m & 1) * 8 + r, dims (2 jp + (m >> 1)) * 8
+        const uint32_t addr = vs_addr + ((mtx & 1) * 8 + r) * VPITCH + (2 * jp + (mtx >> 1)) * 16;
+        uint32_t b[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float d2 = 0.f, d3 = 0.f;                          // rows 8..15 of the tile: unused
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(o[2 * jp + h][0]), "+f"(o[2 * jp + h][1]), "+f"(d2), "+f"(d3)
+                       : "r"(pa0), "r"(0u), "r"(pa2), "r"(0u), "r"(b[2 * h]), "r"(b[2 * h + 1]));
+        }
+      }
+      __syncwarp();                                          // the staging rows are rewritten by the next block
+    }
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    if (g < n_tail) {
+      const float inv = 1.f / l_run;
+      const int row = row0 + g;
+      const int s_idx = (int)(sh / p.heads), h = (int)(sh - (long long)s_idx * p.heads);
+      __nv_bfloat16* ob = p.o + (((size_t)s_idx * NTL + (row >> 7)) * (p.heads * OC) + (size_t)h * OC) * 1024 +
+                          (size_t)(row & 127) * 8 + 2 * t;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        *reinterpret_cast<uint32_t*>(ob + (size_t)j * 1024) = tc::pack_bf16(o[j][0] * inv, o[j][1] * inv);
+    }
+  }
+}
+
 inline uint32_t attn_tc_smem(int HDP) {
   return (uint32_t)(4 + ATT_STAGES * 2) * HDP * 128 * 2 + 4 * 128 * 64 * 2 + 512;
 }
@@ -480,6 +600,10 @@ __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* 
   }
 }
 
+#ifndef QKV_L2_PREFETCH
+#define QKV_L2_PREFETCH 1
+#endif
+constexpr int QKV_PF_DIST = 2;
 constexpr int QKV_PRODUCER_WARPS = 8;
 #ifndef QKV_UF
 #define QKV_UF 8   // (8-row, group) units a producer lane keeps in flight (4: two round trips per tile, r01)
@@ -499,6 +623,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
   constexpr int NPROD = QKV_PRODUCER_WARPS * 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + 8 * 16);
   if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile int*>(smem + off_bar + 8 * 18) = 0;
     mbar_init(BAR(W_FULL), 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1);
@@ -518,6 +643,37 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       mbar_arrive_expect_tx(BAR(W_FULL), 3 * part_bytes);
       for (int i = 0; i < 3; ++i) bulk_g2s(sbase + off_w + i * part_bytes, p.wimg + (size_t)i * part_bytes, part_bytes, BAR(W_FULL));
     }
+#if QKV_L2_PREFETCH
+    // L2 prefetch of the x rows of the tiles ahead: the producers keep a whole tile (64 KB) in flight, but only while
+    // they load -- not while they normalise -- so HBM latency capped the kernel at ~4 TB/s.  This warp follows the
+    // producers (it observes A_FULL) and requests the rows of the tile QKV_PF_DIST tiles further on.
+    auto prefetch_tile = [&](int it) {
+      if (it >= n_iter) return;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = tile / NTL, jt = tile - s * NTL;
+      const int rows = min(128, p.L - jt * 128);
+      const float* src = p.x + p.map.base(s) + (long long)(jt * 128) * p.map.pos_stride;
+      if (p.map.pos_stride == C) {                 // rows are contiguous: a few large requests
+        const uint32_t total = (uint32_t)rows * C * 4;
+        for (uint32_t off = lane * 8192u; off < total; off += 32 * 8192u)
+          bulk_prefetch_l2(reinterpret_cast<const char*>(src) + off, min(8192u, total - off));
+      } else {
+        for (int r = lane; r < rows; r += 32) bulk_prefetch_l2(src + (long long)r * p.map.pos_stride, (uint32_t)C * 4);
+      }
+    };
+    // Pacing by a progress word the producers publish (not by a barrier: a prefetcher that falls a ring turn behind
+    // must skip ahead, which a parity wait cannot express).
+    volatile int* progress = reinterpret_cast<volatile int*>(smem + off_bar + 8 * 18);
+    int next = 1;                                   // next tile (local index) to request
+    for (;;) {
+      const int done = *progress;                   // tiles the producers have finished
+      const int want = min(n_iter, done + 1 + QKV_PF_DIST);
+      if (next < done + 1) next = done + 1;         // fell behind: those rows are being read already
+      for (; next < want; ++next) prefetch_tile(next);
+      if (done >= n_iter - 1 || next >= n_iter) break;
+      __nanosleep(200);
+    }
+#endif
   } else if (warp == 1) {
     {
       const uint32_t idesc = instr_desc(128, NPART);
@@ -667,6 +823,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       }
       fence_proxy_async();
       mbar_arrive(BAR(A_FULL + slot));
+      if (tp == 0) *reinterpret_cast<volatile int*>(smem + off_bar + 8 * 18) = it + 1;   // progress word of the L2 prefetcher
       if (++slot == 3) { slot = 0; ph ^= 1; }
     }
   } else {

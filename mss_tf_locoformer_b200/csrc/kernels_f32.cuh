@@ -171,65 +171,6 @@ __global__ void __launch_bounds__(256) enc_conv_kernel(const float* __restrict__
   }
 }
 
-// Register-weight variant (C/4 divides 256): a thread keeps its channel quad for the whole launch, so the 9 * CIN weight
-// vectors live in registers instead of being re-read from shared memory for every position (the shared-memory version
-// spends 18 LDS.128 per 72 FMAs: ncu r02 had it at 77 % SM throughput, 16 % of the HBM write peak).  The C/4 threads of
-// a position read the same 9 * CIN inputs (broadcast loads served by L1).  Same arithmetic order as the kernel above.
-template <int CIN>
-__global__ void __launch_bounds__(256) enc_conv_reg_kernel(const float* __restrict__ spec, int n_frames, int n_freq,
-                                                           int C, const float* __restrict__ w /*[3][3][CIN][C]*/,
-                                                           const float* __restrict__ bias, float* __restrict__ y,
-                                                           double* __restrict__ partial /*[B][gridDim.x][2]*/) {
-  const int b = blockIdx.y;
-  const int c4n = C >> 2;
-  const int c = (threadIdx.x % c4n) << 2;
-  const int ppb = 256 / c4n;                                  // positions per block and pass
-  float4 wr[9 * CIN];
-#pragma unroll
-  for (int i = 0; i < 9 * CIN; ++i) wr[i] = __ldg(reinterpret_cast<const float4*>(w + (size_t)i * C + c));
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
-  const long long n_pos = (long long)n_frames * n_freq;
-  const float* in = spec + (size_t)b * n_pos * CIN;
-  float* out = y + (size_t)b * n_pos * C;
-  double s1 = 0.0, s2 = 0.0;
-  for (long long pos = (long long)blockIdx.x * ppb + threadIdx.x / c4n; pos < n_pos; pos += (long long)gridDim.x * ppb) {
-    const int f = (int)(pos % n_freq), t = (int)(pos / n_freq);
-    float4 a = bv;
-#pragma unroll
-    for (int dt = 0; dt < 3; ++dt) {
-      const int tt = t + dt - 1;
-      if (tt < 0 || tt >= n_frames) continue;
-#pragma unroll
-      for (int df = 0; df < 3; ++df) {
-        const int ff = f + df - 1;
-        if (ff < 0 || ff >= n_freq) continue;
-        const float* px = in + ((size_t)tt * n_freq + ff) * CIN;
-#pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-          const float xv = __ldg(&px[ci]);
-          const float4 wv = wr[(dt * 3 + df) * CIN + ci];
-          a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y);
-          a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
-        }
-      }
-    }
-    *reinterpret_cast<float4*>(&out[pos * C + c]) = a;
-    s1 += (double)a.x + (double)a.y + (double)a.z + (double)a.w;
-    s2 += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
-  }
-  __shared__ double r1[256], r2[256];
-  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = r1[0];
-    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r2[0];
-  }
-}
-
 __global__ void gln_finalize_kernel(const double* __restrict__ partial, int n_part, double count, float eps,
                                     float* __restrict__ stats /*[B][2] mean, rstd*/) {
   const int b = blockIdx.x;

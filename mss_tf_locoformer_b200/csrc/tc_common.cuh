@@ -119,6 +119,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// bulk prefetch of a contiguous global range into L2 (no registers, no shared memory, no completion to wait for):
+// used to pull the fp32 residual rows a producer warp will read two tiles from now, so that its loads -- whose number
+// in flight is bounded by registers -- hit L2 instead of HBM.  16-byte aligned address, size a multiple of 16.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

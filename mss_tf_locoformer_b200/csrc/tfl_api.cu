@@ -19,7 +19,7 @@
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {0}};   // tfl_debug_set_option
+static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}};   // tfl_debug_set_option
 int tfl_option(int key) { return g_options[key].load(std::memory_order_relaxed); }
 std::atomic<unsigned long long> g_launches{0};
 
@@ -447,7 +447,14 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       kern<<<grid, ATT2_THREADS, smem, st>>>(a2);
     }
     TFL_LAUNCH_CHECK();
-    if (tail_q) {
+    if (tail_q && tfl_option(TFL_OPT_TAIL_KERNEL) != 1) {
+      // warp-level tensor-core path: one warp per (sequence, head), all tail rows at once
+      long long blocks = ((long long)nseq * heads + 7) / 8;
+      if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
+      if (HDP == 16) attn_tail_mma_kernel<1><<<(int)blocks, 256, 0, st>>>(ap, ap.NQT * 128);
+      else attn_tail_mma_kernel<2><<<(int)blocks, 256, 0, st>>>(ap, ap.NQT * 128);
+      TFL_LAUNCH_CHECK();
+    } else if (tail_q) {
       const long long warps = (long long)nseq * heads * tail_q;
       long long blocks = (warps + 7) / 8;
       if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
@@ -549,12 +556,8 @@ int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, 
   double* part = (double*)(wsp + ws.gln_part);
   float* stats = (float*)(wsp + ws.gln_stats);
   const size_t smem = ((size_t)9 * 2 * C + C) * sizeof(float);
-  if (C % 4 == 0 && 256 % (C / 4) == 0)
-    enc_conv_reg_kernel<2><<<dim3(ws.gln_blocks, B), 256, 0, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
-                                                                  (const float*)(base + pl->lay.enc_b), x, part);
-  else
-    enc_conv_kernel<2><<<dim3(ws.gln_blocks, B), 256, smem, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
-                                                                (const float*)(base + pl->lay.enc_b), x, part);
+  enc_conv_kernel<2><<<dim3(ws.gln_blocks, B), 256, smem, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
+                                                              (const float*)(base + pl->lay.enc_b), x, part);
   TFL_LAUNCH_CHECK();
   gln_finalize_kernel<<<B, 256, 0, st>>>(part, ws.gln_blocks, (double)Tf * F * C, c.eps, stats);
   TFL_LAUNCH_CHECK();

@@ -6,4 +6,4 @@ for n in clrel clwait; do echo "== $n"; TFL_LIB=$V/lib_$n.so timeout 200 python 
 echo "== default again"; timeout 200 python profiles/time_kernels.py 8 2>&1 | tail -3
 timeout 300 python profiles/trace_ffn.py 8 300 > gpurun_out/r02_trace_ffn_b8_q300_b.txt 2>&1; sed -n 4,16p gpurun_out/r02_trace_ffn_b8_q300_b.txt
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_n1_d.json 2> gpurun_out/r02_bench_n1_d.err; cat gpurun_out/r02_bench_n1_d.json | cut -c1-1200; tail -3 gpurun_out/r02_bench_n1_d.err
-bash profiles/scripts/sanitize.sh
+
