@@ -463,28 +463,50 @@ __global__ void __launch_bounds__(256) attn_tail_mma_kernel(AttnTcParams p, int 
 #pragma unroll
     for (int j = 0; j < NT; ++j) o[j][0] = o[j][1] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    for (int k0 = 0; k0 < p.L; k0 += 16) {
+    // K fragments and V pieces of the NEXT 16-key block are requested before the current block is processed (one
+    // global round trip per block would otherwise be exposed: 65 of them for a 1025-bin sequence)
+    constexpr int VP = (2 * KS * 16 + 31) / 32;               // 16-byte V pieces per lane and block
+    uint32_t kf[2][KS][2], kf_n[2][KS][2];
+    uint4 vp[VP], vp_n[VP];
+    auto fetch = [&](int k0, uint32_t (&kq)[2][KS][2], uint4 (&vq)[VP]) {
       const size_t tile_off = (size_t)(k0 >> 7) * HDP * 128;
       const int kr = k0 & 127;
-      // stage the 16 V rows of this block: OC chunks x 16 keys x 16 B, coalesced 16-byte pieces
-      for (int piece = lane; piece < OC * 16; piece += 32) {
+#pragma unroll
+      for (int i = 0; i < VP; ++i) {
+        const int piece = lane + 32 * i;
         const int c = piece >> 4, key = piece & 15;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(vimg + tile_off + ((size_t)c * 128 + kr + key) * 8));
-        *reinterpret_cast<uint4*>(vs + key * VPITCH + c * 16) = v;
+        vq[i] = piece < OC * 16 ? __ldg(reinterpret_cast<const uint4*>(vimg + tile_off + ((size_t)c * 128 + kr + key) * 8))
+                                : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const __nv_bfloat16* kt = kimg + tile_off + (size_t)(kr + 8 * n + g) * 8 + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          kq[n][ks][0] = __ldg(reinterpret_cast<const uint32_t*>(kt + (size_t)(2 * ks) * 1024));
+          kq[n][ks][1] = __ldg(reinterpret_cast<const uint32_t*>(kt + (size_t)(2 * ks + 1) * 1024));
+        }
+      }
+    };
+    fetch(0, kf, vp);
+    for (int k0 = 0; k0 < p.L; k0 += 16) {
+      if (k0 + 16 < p.L) fetch(k0 + 16, kf_n, vp_n);
+      // stage the 16 V rows of this block: OC chunks x 16 keys x 16 B
+#pragma unroll
+      for (int i = 0; i < VP; ++i) {
+        const int piece = lane + 32 * i;
+        if (piece < OC * 16) *reinterpret_cast<uint4*>(vs + (piece & 15) * VPITCH + (piece >> 4) * 16) = vp[i];
       }
       // ---- S = Q K^T for keys k0 .. k0 + 15 (two n-tiles of 8 keys) ----
       float sc[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
         sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
-        const __nv_bfloat16* kt = kimg + tile_off + (size_t)(kr + 8 * n + g) * 8 + 2 * t;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(kt + (size_t)(2 * ks) * 1024));
-          const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(kt + (size_t)(2 * ks + 1) * 1024));
           asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                        : "+f"(sc[n][0]), "+f"(sc[n][1]), "+f"(sc[n][2]), "+f"(sc[n][3])
-                       : "r"(qa[ks][0]), "r"(0u), "r"(qa[ks][1]), "r"(0u), "r"(b0), "r"(b1));
+                       : "r"(qa[ks][0]), "r"(0u), "r"(qa[ks][1]), "r"(0u), "r"(kf[n][ks][0]), "r"(kf[n][ks][1]));
         }
       }
       // ---- online softmax on row g (this lane holds keys k0 + 8n + 2t, +1) ----
@@ -525,6 +547,12 @@ __global__ void __launch_bounds__(256) attn_tail_mma_kernel(AttnTcParams p, int 
         }
       }
       __syncwarp();                                          // the staging rows are rewritten by the next block
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) { kf[n][ks][0] = kf_n[n][ks][0]; kf[n][ks][1] = kf_n[n][ks][1]; }
+#pragma unroll
+      for (int i = 0; i < VP; ++i) vp[i] = vp_n[i];
     }
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);

@@ -30,6 +30,12 @@ __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__
   }
 }
 
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ int bitrev(int i, int log_n) { return (int)(__brev((unsigned)i) >> (32 - log_n)); }
 
 // --------------------------------------------------------------------------------------
@@ -58,25 +64,51 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ aud
 }
 
 // --------------------------------------------------------------------------------------
-// K7 istft_ola: one CTA per (hop block, source, batch).  For each frame overlapping the
-// block: Hermitian-extend, inverse FFT in smem, window, accumulate; then divide by the
-// sum of squared windows and store (:56-75).  Output audio[src][b][n].
+// K7 istft_ola: one CTA per (run of ISTFT_RUN hop blocks, source, batch).  For each frame overlapping the
+// run: Hermitian-extend, inverse FFT in smem, window, accumulate; then divide by the sum of squared windows
+// and store (:56-75).  Output audio[src][b][n].  A run of 8 blocks needs 8 + n_fft/hop - 1 inverse FFTs
+// (9 at hop = n_fft/2) where one CTA per block needed n_fft/hop each (16): the FFT passes were what the
+// kernel spent its time on (ncu r02: shared-memory pipe 99 % busy).  Frames are added in increasing
+// order: deterministic.  Twiddles are staged in shared memory once per CTA.
 // --------------------------------------------------------------------------------------
+constexpr int ISTFT_RUN = 8;   // hop blocks per CTA (fewer when shared memory is short: very large hop_length)
+template <bool INVERSE>
+__device__ __forceinline__ void fft_smem_tw(float2* buf, const float2* tws, int n, int log_n) {
+  for (int s = 1; s <= log_n; ++s) {
+    const int half = 1 << (s - 1);
+    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+      const int j = i & (half - 1);
+      const int a = ((i >> (s - 1)) << s) + j;
+      const int b = a + half;
+      float2 w = tws[j << (log_n - s)];
+      if (INVERSE) w.y = -w.y;
+      const float2 u = buf[a], v = buf[b];
+      const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
+      buf[a] = make_float2(u.x + tr, u.y + ti);
+      buf[b] = make_float2(u.x - tr, u.y - ti);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ est, int n_src, int n_frames,
                                                         int n_fft, int log_n, int hop, int n_samples,
                                                         const float2* __restrict__ tw,
                                                         const float* __restrict__ win, float* __restrict__ audio,
-                                                        int batch) {
-  extern __shared__ float2 fbuf[];
-  float* acc = reinterpret_cast<float*>(fbuf + n_fft);
-  float* env = acc + hop;
-  const int m = blockIdx.x, src = blockIdx.y, b = blockIdx.z;
+                                                        int batch, int run) {
+  extern __shared__ float2 fbuf[];                       // n_fft | twiddles n_fft/2 | acc run*hop | env run*hop
+  float2* tws = fbuf + n_fft;
+  float* acc = reinterpret_cast<float*>(tws + (n_fft >> 1));
+  const int span = run * hop;
+  float* env = acc + span;
+  const int m0 = blockIdx.x * run, src = blockIdx.y, b = blockIdx.z;
   const int pad = n_fft >> 1, n_freq = pad + 1;
-  const int q_lo = m * hop + pad;  // padded-signal coordinate of the block's first sample
-  for (int i = threadIdx.x; i < hop; i += blockDim.x) { acc[i] = 0.f; env[i] = 0.f; }
+  const int q_lo = m0 * hop + pad;                       // padded-signal coordinate of the run's first sample
+  for (int i = threadIdx.x; i < (n_fft >> 1); i += blockDim.x) tws[i] = __ldg(&tw[i]);
+  for (int i = threadIdx.x; i < span; i += blockDim.x) { acc[i] = 0.f; env[i] = 0.f; }
   int t_min = (q_lo - n_fft) / hop + 1;
   if (q_lo - n_fft < 0) t_min = 0;
-  int t_max = (q_lo + hop - 1) / hop;
+  int t_max = (q_lo + span - 1) / hop;
   if (t_max > n_frames - 1) t_max = n_frames - 1;
   const float inv_n = 1.f / (float)n_fft;
   for (int t = t_min; t <= t_max; ++t) {
@@ -93,19 +125,20 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict_
       }
     }
     __syncthreads();
-    fft_smem<true>(fbuf, tw, n_fft, log_n);
-    for (int i = threadIdx.x; i < hop; i += blockDim.x) {
+    fft_smem_tw<true>(fbuf, tws, n_fft, log_n);
+    // samples of this frame that fall into the run: padded coordinate t * hop + off, off in [0, n_fft)
+    const int lo = max(0, t * hop - q_lo), hi = min(span, t * hop + n_fft - q_lo);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
       const int off = q_lo + i - t * hop;
-      if (off >= 0 && off < n_fft) {
-        const float w = __ldg(&win[off]);
-        acc[i] += fbuf[off].x * inv_n * w;
-        env[i] += w * w;
-      }
+      const float w = __ldg(&win[off]);
+      acc[i] += fbuf[off].x * inv_n * w;
+      env[i] += w * w;
     }
   }
+  __syncthreads();
   float* out = audio + ((size_t)src * batch + b) * n_samples;
-  for (int i = threadIdx.x; i < hop; i += blockDim.x) {
-    const int n = m * hop + i;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int n = m0 * hop + i;
     if (n < n_samples) out[n] = acc[i] / env[i];
   }
 }
@@ -158,6 +191,110 @@ __global__ void __launch_bounds__(256) enc_conv_kernel(const float* __restrict__
     s1 += (double)a.x + (double)a.y + (double)a.z + (double)a.w;
     s2 += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
   }
+  __shared__ double r1[256], r2[256];
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = r1[0];
+    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = r2[0];
+  }
+}
+
+// K2 (bf16 mode) on the warp-level tensor cores: M = 16 consecutive bins of a frame, N = C outputs in 8-wide
+// n-tiles, K = 9 * CIN = 18 input taps padded to 24 (three m16n8k8 tf32 steps).  The CUDA-core kernel above issues
+// 18 shared-memory weight reads per 72 FMAs and ran at 16 % of the HBM write peak (ncu r02); here a warp task costs
+// ~50 MMAs and the kernel is bound by its 4 * N * C byte store.  tf32 rounding of the spectrogram and the weights
+// (2^-11) -- TFL_PRECISION_BF16 only; the gLN statistics are accumulated in double from the fp32 accumulators.
+// Weight rows in shared memory are padded to C + 8 floats: the four k rows a warp reads then fall into distinct banks.
+// Two passes of the same kernel replace conv -> store -> gLN read-modify-write: PASS 0 only accumulates the statistics
+// (nothing is stored: the conv costs ~50 MMAs per 16 bins), PASS 1 recomputes the conv and stores
+// (v - mean) * rstd * gln_w + gln_b.  HBM traffic of the encoder: one 4 * N * C byte store instead of three passes.
+template <int CIN, int PASS>
+__global__ void __launch_bounds__(256) enc_conv_mma_kernel(const float* __restrict__ spec, int n_frames, int n_freq,
+                                                           int C, const float* __restrict__ w /*[9*CIN][C]*/,
+                                                           const float* __restrict__ bias, float* __restrict__ y,
+                                                           double* __restrict__ partial /*[B][gridDim.x][2]*/,
+                                                           const float* __restrict__ stats /*[B][2] mean, rstd*/,
+                                                           const float* __restrict__ gw, const float* __restrict__ gb) {
+  constexpr int KP = 24;                                      // 9 * CIN = 18 rounded up to a multiple of 8
+  static_assert(9 * CIN <= KP, "tap count");
+  extern __shared__ float wsm[];                              // [KP][C + 8] tf32-rounded, rows >= 9 * CIN zero; bias [C]; PASS 1: scale, shift [C]
+  const int WP = C + 8;
+  for (int i = threadIdx.x; i < KP * WP; i += blockDim.x) {
+    const int k = i / WP, c = i - k * WP;
+    wsm[i] = (k < 9 * CIN && c < C) ? __uint_as_float(to_tf32(w[k * C + c])) : 0.f;
+  }
+  float* bsm = wsm + KP * WP;
+  const int b = blockIdx.y;
+  float* scl = bsm + C;
+  float* sft = scl + C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    bsm[i] = bias[i];
+    if (PASS == 1) { const float rstd = stats[b * 2 + 1]; scl[i] = rstd * gw[i]; sft[i] = gb[i] - stats[b * 2] * rstd * gw[i]; }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int NG = (n_freq + 15) / 16;
+  const long long n_tiles = (long long)n_frames * NG;
+  const float* in = spec + (size_t)b * n_frames * n_freq * CIN;
+  float* out = y + (size_t)b * n_frames * n_freq * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long tile = (long long)blockIdx.x * wpb + warp; tile < n_tiles; tile += (long long)gridDim.x * wpb) {
+    const int t = (int)(tile / NG), f0 = (int)(tile - (long long)t * NG) * 16;
+    // A fragments: row position f0 + g (+ 8), k = 8 s + t4 (+ 4) -> tap k / CIN, channel k % CIN
+    uint32_t a[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                           // h: k-slot t4 / t4 + 4
+        const int k = 8 * s + t4 + 4 * h;
+        const int tap = k / CIN, ci = k - tap * CIN;
+        const int dt = tap / 3, df = tap - dt * 3;
+        const int tt = t + dt - 1;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                         // r: tile row g / g + 8
+          const int ff = f0 + g + 8 * r + df - 1;
+          const bool ok = k < 9 * CIN && tt >= 0 && tt < n_frames && ff >= 0 && ff < n_freq;
+          a[s][2 * h + r] = ok ? to_tf32(__ldg(&in[((size_t)tt * n_freq + ff) * CIN + ci])) : 0u;
+        }
+      }
+    const bool va = f0 + g < n_freq, vb = f0 + g + 8 < n_freq;
+    float* oa = out + ((size_t)t * n_freq + f0 + g) * C + 2 * t4;
+    float* ob = oa + (size_t)8 * C;
+    for (int j = 0; j < C / 8; ++j) {
+      const float2 bb = *reinterpret_cast<const float2*>(bsm + 8 * j + 2 * t4);
+      float acc[4] = {bb.x, bb.y, bb.x, bb.y};
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const uint32_t b0 = __float_as_uint(wsm[(8 * s + t4) * WP + 8 * j + g]);
+        const uint32_t b1 = __float_as_uint(wsm[(8 * s + t4 + 4) * WP + 8 * j + g]);
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                     : "r"(a[s][0]), "r"(a[s][1]), "r"(a[s][2]), "r"(a[s][3]), "r"(b0), "r"(b1));
+      }
+      if (PASS == 0) {
+        if (va) {
+          s1 += (double)acc[0] + (double)acc[1];
+          s2 += (double)acc[0] * acc[0] + (double)acc[1] * acc[1];
+        }
+        if (vb) {
+          s1 += (double)acc[2] + (double)acc[3];
+          s2 += (double)acc[2] * acc[2] + (double)acc[3] * acc[3];
+        }
+      } else {
+        const float2 sc = *reinterpret_cast<const float2*>(scl + 8 * j + 2 * t4);
+        const float2 sh = *reinterpret_cast<const float2*>(sft + 8 * j + 2 * t4);
+        if (va) *reinterpret_cast<float2*>(oa + 8 * j) = make_float2(fmaf(acc[0], sc.x, sh.x), fmaf(acc[1], sc.y, sh.y));
+        if (vb) *reinterpret_cast<float2*>(ob + 8 * j) = make_float2(fmaf(acc[2], sc.x, sh.x), fmaf(acc[3], sc.y, sh.y));
+      }
+    }
+  }
+  if (PASS != 0) return;
   __shared__ double r1[256], r2[256];
   r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
   __syncthreads();
@@ -543,6 +680,82 @@ __global__ void __launch_bounds__(256, 2) dec_conv_kernel(const float* __restric
     if (f < n_freq && o < n_out) {
       const int src = o >> 1, ri = o & 1;
       est[(((((size_t)b * n_src + src) * n_frames + t) * n_freq + f) << 1) + ri] = acc[0] + __ldg(&bias[o]);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// K6 (bf16 mode) decoder on the warp-level tensor cores: the transposed conv is an implicit GEMM with
+// M = positions, N = 8 outputs, K = 9 taps x C -- N = 8 is exactly mma.sync m16n8k8 (tf32 operands, fp32
+// accumulation), a shape the M >= 64 / N >= 16 tcgen05 path cannot use without 2-8x padding.  The CUDA-core
+// kernel above is bound by its shared-memory weight reads and FMA issue together (1.6 ms, ncu r02); here a
+// warp owns 16 consecutive bins of one frame and spends 2 global loads + 1 shared load per two MMAs.
+// K order inside an MMA is free (a sum over channels): lane (g, t) feeds channels 4t .. 4t+3 of a
+// 16-channel step as k-slots (t, t+4) of two MMAs, so x and w arrive as 128-bit loads.
+// Operands are rounded to tf32 (cvt.rna): relative error 2^-11 per product, ~25 dB below the bf16 rounding of
+// the blocks that feed this layer -- used in TFL_PRECISION_BF16 only; fp32 mode keeps dec_conv_kernel.
+// wd layout: [9 taps][8 outputs][C] (tap = dt*3+df multiplies x[t+1-dt, f+1-df]).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_conv_mma_kernel(const float* __restrict__ x, int n_frames, int n_freq, int C,
+                                                           int n_out, const float* __restrict__ wd,
+                                                           const float* __restrict__ bias, float* __restrict__ est,
+                                                           long long n_rows /* B * Tf */) {
+  extern __shared__ float wsm[];  // 9*8*C, tf32-rounded
+  for (int i = threadIdx.x; i < 9 * C * 8; i += blockDim.x) wsm[i] = __uint_as_float(to_tf32(wd[i]));
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n_src = n_out >> 1;
+  const int NG = (n_freq + 15) / 16;                           // 16-bin tiles per frame
+  // A block works on a patch of wpb consecutive frames x 16 bins, one frame per warp: the three time taps of
+  // neighbouring frames then hit the same SM's L1 (with frames spread over blocks every x row came from L2 three
+  // times and the kernel was L2-bandwidth bound: 0.99 ms).
+  const int TG = (n_frames + wpb - 1) / wpb;                   // frame groups per sample
+  const long long n_patches = (n_rows / n_frames) * TG * NG;
+  const float b0 = 2 * t4 < n_out ? __ldg(&bias[2 * t4]) : 0.f, b1 = 2 * t4 + 1 < n_out ? __ldg(&bias[2 * t4 + 1]) : 0.f;
+  for (long long patch = blockIdx.x; patch < n_patches; patch += gridDim.x) {
+    const int f0 = (int)(patch % NG) * 16;
+    const long long r = patch / NG;
+    const int t = (int)(r % TG) * wpb + warp, b = (int)(r / TG);
+    if (t >= n_frames) continue;
+    float acc[4] = {b0, b1, b0, b1};                           // rows g and g + 8, outputs 2 t4, 2 t4 + 1
+#pragma unroll 1
+    for (int dt = 0; dt < 3; ++dt) {
+      const int tt = t + 1 - dt;
+      if (tt < 0 || tt >= n_frames) continue;
+      const float* prow = x + (((size_t)b * n_frames + tt) * n_freq) * C;
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        const int fa = f0 + g + 1 - df, fb = fa + 8;           // input bins of tile rows g and g + 8
+        const bool va = fa >= 0 && fa < n_freq, vb = fb >= 0 && fb < n_freq;
+        const float* pa = prow + (size_t)(va ? fa : 0) * C + 4 * t4;
+        const float* pb = prow + (size_t)(vb ? fb : 0) * C + 4 * t4;
+        const float* pw = wsm + ((dt * 3 + df) * 8 + g) * C + 4 * t4;
+#pragma unroll 4
+        for (int c0 = 0; c0 < C; c0 += 16) {
+          const float4 xa = va ? __ldg(reinterpret_cast<const float4*>(pa + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 xb = vb ? __ldg(reinterpret_cast<const float4*>(pb + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 w = *reinterpret_cast<const float4*>(pw + c0);
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                       : "r"(to_tf32(xa.x)), "r"(to_tf32(xb.x)), "r"(to_tf32(xa.y)), "r"(to_tf32(xb.y)),
+                         "r"(__float_as_uint(w.x)), "r"(__float_as_uint(w.y)));
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                       : "r"(to_tf32(xa.z)), "r"(to_tf32(xb.z)), "r"(to_tf32(xa.w)), "r"(to_tf32(xb.w)),
+                         "r"(__float_as_uint(w.z)), "r"(__float_as_uint(w.w)));
+        }
+      }
+    }
+    if (2 * t4 < n_out) {
+      const int src = t4;                                      // outputs (2 src, 2 src + 1) = (re, im) of source src
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int f = f0 + g + 8 * h;
+        if (f < n_freq)
+          *reinterpret_cast<float2*>(est + ((((size_t)b * n_src + src) * n_frames + t) * n_freq + f) * 2) =
+              make_float2(acc[2 * h], acc[2 * h + 1]);
+      }
     }
   }
 }

@@ -447,7 +447,9 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       kern<<<grid, ATT2_THREADS, smem, st>>>(a2);
     }
     TFL_LAUNCH_CHECK();
-    if (tail_q && tfl_option(TFL_OPT_TAIL_KERNEL) != 1) {
+    // one tail row (frequency axis of n_fft 2048: 1025 = 8 * 128 + 1) has nothing to share between rows and long key
+    // ranges: the CUDA-core kernel is at its K / V traffic floor there (0.20 ms vs 0.25 ms, r02); several rows: mma.sync
+    if (tail_q >= 2 && tfl_option(TFL_OPT_TAIL_KERNEL) != 1) {
       // warp-level tensor-core path: one warp per (sequence, head), all tail rows at once
       long long blocks = ((long long)nseq * heads + 7) / 8;
       if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
@@ -541,8 +543,20 @@ int tfl_stft(const tfl_plan* pl, const void* packed, const float* audio, int B, 
   return 0;
 }
 
+}  // extern "C"
+namespace tfl {
+static int enc_conv_gln_any(const tfl_plan* pl, const void* packed, const float* spec, int B, int Tf, int F, float* x,
+                            void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream);
+}
+extern "C" {
 int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, int B, int Tf, int F, float* x,
                      void* workspace, size_t ws_bytes, tfl_stream_t stream) {
+  return enc_conv_gln_any(pl, packed, spec, B, Tf, F, x, workspace, ws_bytes, TFL_PRECISION_FP32, stream);
+}
+}  // extern "C"
+namespace tfl {
+static int enc_conv_gln_any(const tfl_plan* pl, const void* packed, const float* spec, int B, int Tf, int F, float* x,
+                            void* workspace, size_t ws_bytes, int precision, tfl_stream_t stream) {
   NvtxRange nvtx_range("tfl::enc_conv_gln");
   if (check_common(pl, packed, B, Tf, F, 0)) return -1;
   TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv encoder");
@@ -556,6 +570,22 @@ int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, 
   double* part = (double*)(wsp + ws.gln_part);
   float* stats = (float*)(wsp + ws.gln_stats);
   const size_t smem = ((size_t)9 * 2 * C + C) * sizeof(float);
+  if (precision == TFL_PRECISION_BF16 && C % 8 == 0) {   // tf32 mma.sync path, two passes (see enc_conv_mma_kernel)
+    const size_t msm = ((size_t)24 * (C + 8) + 3 * C) * sizeof(float);
+    TFL_CUDA(opt_in_smem(enc_conv_mma_kernel<2, 0>, msm));
+    TFL_CUDA(opt_in_smem(enc_conv_mma_kernel<2, 1>, msm));
+    const float* ew = (const float*)(base + pl->lay.enc_w);
+    const float* eb = (const float*)(base + pl->lay.enc_b);
+    const float* gw = (const float*)(base + pl->lay.gln_w);
+    const float* gb = (const float*)(base + pl->lay.gln_b);
+    enc_conv_mma_kernel<2, 0><<<dim3(ws.gln_blocks, B), 256, msm, st>>>(spec, Tf, F, C, ew, eb, x, part, nullptr, gw, gb);
+    TFL_LAUNCH_CHECK();
+    gln_finalize_kernel<<<B, 256, 0, st>>>(part, ws.gln_blocks, (double)Tf * F * C, c.eps, stats);
+    TFL_LAUNCH_CHECK();
+    enc_conv_mma_kernel<2, 1><<<dim3(ws.gln_blocks, B), 256, msm, st>>>(spec, Tf, F, C, ew, eb, x, part, stats, gw, gb);
+    TFL_LAUNCH_CHECK();
+    return 0;
+  }
   enc_conv_kernel<2><<<dim3(ws.gln_blocks, B), 256, smem, st>>>(spec, Tf, F, C, (const float*)(base + pl->lay.enc_w),
                                                               (const float*)(base + pl->lay.enc_b), x, part);
   TFL_LAUNCH_CHECK();
@@ -567,6 +597,9 @@ int tfl_enc_conv_gln(const tfl_plan* pl, const void* packed, const float* spec, 
   TFL_LAUNCH_CHECK();
   return 0;
 }
+
+}  // namespace tfl
+extern "C" {
 
 int tfl_rms_group_norm(const tfl_plan* pl, const void* packed, int layer, int axis, int which, const float* x,
                        float* y, int64_t rows, tfl_stream_t stream) {
@@ -626,6 +659,31 @@ int tfl_rope_attn(const tfl_plan* pl, const void* packed, int layer, int axis, f
   return attn_f32(pl, (const char*)packed, layer, axis, x, Dims{B, Tf, F}, ws, (char*)workspace, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+namespace tfl {
+// bf16 mode: tf32 mma.sync decoder (C % 16 == 0); fp32 mode and odd widths: the CUDA-core kernel (tfl_dec_conv)
+static int dec_conv_any(const tfl_plan* pl, const void* packed, const float* x, int B, int Tf, int F, float* est,
+                        int precision, tfl_stream_t stream) {
+  const int C = pl->cfg.emb_dim;
+  if (precision != TFL_PRECISION_BF16 || C % 16 != 0 || pl->cfg.n_src * 2 > 8) return tfl_dec_conv(pl, packed, x, B, Tf, F, est, stream);
+  NvtxRange nvtx_range("tfl::dec_conv[tf32]");
+  if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  const size_t smem = (size_t)9 * C * 8 * sizeof(float);
+  TFL_CUDA(opt_in_smem(dec_conv_mma_kernel, smem));
+  const char* base = (const char*)packed;
+  long long blocks = (long long)B * ((Tf + 7) / 8) * ((F + 15) / 16);   // patches of 8 frames x 16 bins
+  const long long cap = (long long)pl->sm_count * (smem > 56 * 1024 ? 2 : 4);
+  if (blocks > cap) blocks = cap;
+  dec_conv_mma_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, Tf, F, C, pl->cfg.n_src * 2,
+                                                                       (const float*)(base + pl->lay.dec_w),
+                                                                       (const float*)(base + pl->lay.dec_b), est,
+                                                                       (long long)B * Tf);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace tfl
+extern "C" {
+
 int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, int Tf, int F, float* est,
                  tfl_stream_t stream) {
   NvtxRange nvtx_range("tfl::dec_conv");
@@ -653,12 +711,17 @@ int tfl_istft_ola(const tfl_plan* pl, const void* packed, const float* est, int 
   TFL_CHECK(c.n_fft > 0, "plan has no STFT (n_fft == 0)");
   TFL_CHECK(B >= 1 && Tf >= 1 && T >= 1, "empty input");
   const char* base = (const char*)packed;
-  const size_t smem = (size_t)c.n_fft * sizeof(float2) + (size_t)2 * c.hop * sizeof(float);
+  const size_t fixed = (size_t)c.n_fft * sizeof(float2) + (size_t)(c.n_fft / 2) * sizeof(float2);
+  int run = ISTFT_RUN;
+  while (run > 1 && fixed + (size_t)2 * run * c.hop * sizeof(float) > (size_t)160 * 1024) --run;
+  const size_t smem = fixed + (size_t)2 * run * c.hop * sizeof(float);
+  TFL_CHECK(smem <= (size_t)TC_SMEM_MAX, "n_fft / hop_length too large for the iSTFT kernel's shared memory");
   TFL_CUDA(opt_in_smem(istft_ola_kernel, smem));
-  dim3 grid((T + c.hop - 1) / c.hop, c.n_src, B);
+  const int n_blocks = (T + c.hop - 1) / c.hop;
+  dim3 grid((n_blocks + run - 1) / run, c.n_src, B);
   istft_ola_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(est, c.n_src, Tf, c.n_fft, ilog2(c.n_fft), c.hop, T,
                                                               (const float2*)(base + pl->lay.twiddle),
-                                                              (const float*)(base + pl->lay.window), audio, B);
+                                                              (const float*)(base + pl->lay.window), audio, B, run);
   TFL_LAUNCH_CHECK();
   return 0;
 }
@@ -680,9 +743,9 @@ int tfl_separator_forward(const tfl_plan* pl, const void* packed, const float* s
   TFL_CHECK(workspace && ws_bytes >= ws.total, "workspace too small (%zu < %zu)", ws_bytes, ws.total);
   char* wsp = (char*)workspace;
   float* x = (float*)(wsp + ws.x);
-  if (tfl_enc_conv_gln(pl, packed, spec, B, Tf, F, x, workspace, ws_bytes, stream)) return -1;
+  if (enc_conv_gln_any(pl, packed, spec, B, Tf, F, x, workspace, ws_bytes, precision, stream)) return -1;
   if (blocks_forward(pl, (const char*)packed, x, Dims{B, Tf, F}, ws, wsp, precision, (cudaStream_t)stream)) return -1;
-  return tfl_dec_conv(pl, packed, x, B, Tf, F, est, stream);
+  return dec_conv_any(pl, packed, x, B, Tf, F, est, precision, stream);
 }
 
 int tfl_forward(const tfl_plan* pl, const void* packed, const float* mixture, int B, int T, float* audio,
