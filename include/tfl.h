@@ -150,8 +150,11 @@ int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan,
  *   TFL_OPT_FFN_KERNEL   1 = ffn_tc_kernel (two tiles per CTA), 2 = ffn_tc2_kernel (cta_group::2, one tile per CTA of a
  *                        2-CTA cluster; default where the shape allows it)
  *   TFL_OPT_TAIL_KERNEL  1 = attn_tail_rows_kernel (CUDA cores), 2 = attn_tail_mma_kernel (mma.sync; default)
+ *   TFL_OPT_PDL          1 = programmatic dependent launch of the bf16 kernels of a step, 0 = plain launches (default:
+ *                        measured neutral, 97.8 vs 97.8 ms per step -- the persistent kernels leave no SM free to start on)
  *   TFL_OPT_TRACE_BASE   first chunk / tile index the pipeline trace records (64 entries per event; default 0) */
-enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_TRACE_BASE = 2, TFL_OPT_TAIL_KERNEL = 3, TFL_OPT_COUNT = 4 };
+enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_TRACE_BASE = 2, TFL_OPT_TAIL_KERNEL = 3, TFL_OPT_PDL = 4,
+       TFL_OPT_COUNT = 8 };
 int tfl_debug_set_option(int key, int value);
 
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN

@@ -65,6 +65,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("TFL_PDL"):             # A/B: programmatic dependent launch of the bf16 kernels (default off)
+        lib.tfl_debug_set_option(4, 1)
     _lib = lib
     return lib
 

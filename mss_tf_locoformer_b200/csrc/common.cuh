@@ -46,6 +46,26 @@ inline cudaError_t opt_in_smem(Kernel kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Programmatic dependent launch for the back-to-back persistent kernels of a step: the next kernel's CTAs become
+// resident as the previous kernel's CTAs exit and run their prologue (barrier init, TMEM allocation, table loads) while
+// the tail of the previous kernel is still draining; they block in griddep_wait() before touching anything the
+// previous kernel wrote.  tfl_debug_set_option(TFL_OPT_PDL, 0) launches plainly (A/B).
+int tfl_option(int key);
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tfl_option(4 /* TFL_OPT_PDL */) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // Maps (sequence s, position p) of one Locoformer path onto the channels-last residual
 // stream x[B, Tf, F, C] without materialising the reference's transposes
 // (models/mss_tflocoformer.py:339-344): element offset = (s / inner) * outer_stride
@@ -74,6 +94,7 @@ inline SeqMap make_dense_map(long long seq_stride, long long pos_stride) {
   return m;
 }
 
+constexpr int ROPE_TAB_LEN = 2304;   // positions covered by the pack-time RoPE table (F = 2049 of n_fft 4096 fits); longer: per call
 // ---- packed weight image -------------------------------------------------------------
 struct FfnPack {
   size_t gamma;      // [C] fp32
@@ -91,6 +112,7 @@ struct PathPack {
   FfnPack ffn[2];
   size_t attn_gamma, wqkv /*[C][3A]*/, wo /*[A][C]*/, rope /*[hd/2]*/;
   size_t tc_qkv, tc_wo;
+  size_t rope_tab;   // (cos, sin) of positions 0 .. ROPE_TAB_LEN - 1, frequency-major [HDP/2][ROPE_TAB_LEN] float2 (bf16 path)
 };
 struct PackLayout {
   size_t enc_w /*[3][3][Cin][C]*/, enc_b, gln_w, gln_b, dec_w /*[9 taps][8 outputs][C]*/, dec_b;

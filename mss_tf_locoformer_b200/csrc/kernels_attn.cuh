@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(352, 1) attn_tc_kernel(AttnTcParams p) {
 // reduction of the output.  Same bf16 images, same exp2 domain as the tensor-core kernel.
 template <int RG>
 __global__ void __launch_bounds__(256) attn_tail_rows_kernel(AttnTcParams p, int row0) {
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int n_tail = p.L - row0, n_grp = (n_tail + RG - 1) / RG;
   const long long total = (long long)p.nseq * p.heads * n_grp;
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(256) attn_tail_mma_kernel(AttnTcParams p, int 
   constexpr int HDP = 16 * KS, NT = 2 * KS;                  // NT = 8-wide n-tiles of the head dimension
   constexpr int VPITCH = HDP * 2 + 16;                       // bytes per staged V row (padded: conflict-free ldmatrix)
   __shared__ __align__(16) uint8_t vstage[8][16 * VPITCH];
+  griddep_wait();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int n_tail = p.L - row0, NTL = p.NTL, OC = HDP / 8;
@@ -588,7 +590,8 @@ __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ft
 struct QkvTcParams {
   const float* x; SeqMap map; const float* gamma; float eps;
   const char* wimg;                 // [3 parts][C/8 chunks][NPART rows][8] bf16
-  const float2* rope;               // [HDP/2][L] (cos, sin), frequency-major, or nullptr ("nope")
+  const float2* rope;               // [HDP/2][rope_stride] (cos, sin), frequency-major, or nullptr ("nope")
+  int rope_stride;                  // positions per table row (L for a per-call table, ROPE_TAB_LEN for the packed one)
   __nv_bfloat16* qkv;               // tile images
   int C, G, L, NTL, nseq, heads, hd, HDP, NPART;
   int n_tiles;
@@ -665,6 +668,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_iter = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  griddep_wait();                                          // (PDL) the prologue overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -871,7 +875,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       float2 cs[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)i * p.L + j]) : make_float2(1.f, 0.f);
+        cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)i * p.rope_stride + j]) : make_float2(1.f, 0.f);
       // Rows at or beyond ceil64(L) are never read by the attention kernels (attn_tc_kernel masks whole 64-key units,
       // attn_tc2_kernel ends on a ceil16 block, the tail-row kernel reads single query rows): neither loaded from TMEM
       // nor written -- on the time axis (259 rows in three 128-row tiles) that is 17 % of the image.
@@ -954,6 +958,7 @@ __global__ void __launch_bounds__(320, 1) proj_tc_kernel(ProjTcParams p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_iter = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  griddep_wait();                                          // (PDL) the prologue overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {

@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_wait();                                          // (PDL) the prologue overlapped the previous kernel's tail
   const size_t which_stride = (size_t)p.nseq * p.heads * NTL * HDP * 128;   // elements between the q, k, v planes
 
   // item -> (sequence, first head, first query tile); group g -> (head, tile).  Groups 2k and 2k+1 form a PAIR served

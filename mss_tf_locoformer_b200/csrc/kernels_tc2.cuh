@@ -326,6 +326,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
   cluster_sync_all();                                      // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_wait();                                          // (PDL) everything above overlapped the previous kernel's tail
   unsigned long long* const tr = (blockIdx.x == 0 && lane == 0) ? g_trace : nullptr;   // diagnostic event trace
   const int n_cl = (int)n_clusters_x(), cl = (int)cluster_id_x();
   const int n_pairs = (p.n_tiles + 1) / 2;
@@ -660,7 +661,7 @@ inline int tc_ffn2_launch(const tfl_plan* pl, const FfnTcParams& p0, const Ffn2G
   const int n_pairs = (p.n_tiles + 1) / 2;
   int clusters = pl->sm_count / 2;
   if (n_pairs < clusters) clusters = n_pairs;
-  ffn_tc2_kernel<<<2 * clusters, FFN2_THREADS, g.smem_bytes, st>>>(p, g);
+  TFL_CUDA(launch_pdl(ffn_tc2_kernel, dim3(2 * clusters), dim3(FFN2_THREADS), g.smem_bytes, st, p, g));
   TFL_LAUNCH_CHECK();
   return 0;
 }

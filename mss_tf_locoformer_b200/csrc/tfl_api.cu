@@ -19,7 +19,7 @@
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}};   // tfl_debug_set_option
+static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {0}, {0}, {0}};   // tfl_debug_set_option
 int tfl_option(int key) { return g_options[key].load(std::memory_order_relaxed); }
 std::atomic<unsigned long long> g_launches{0};
 
@@ -132,6 +132,8 @@ static void build_layout(tfl_plan* pl) {
     p.wo = take((size_t)A * C);
     p.tc_qkv = take(tc_qkv_image_bytes(C, c.n_heads, pl->head_dim) / sizeof(float));
     p.tc_wo = take(tc_wo_image_bytes(C, c.n_heads, pl->head_dim) / sizeof(float));
+    p.rope_tab = (c.rope && attn_tc_supported(C, c.n_heads, pl->head_dim))
+                     ? take((size_t)ROPE_TAB_LEN * ((pl->head_dim + 15) / 16 * 16 / 2) * 2) : 0;
   }
   L.total = off;
 }
@@ -242,6 +244,11 @@ int tfl_pack_weights(const tfl_plan* pl, const float* const* w, int n_weights, v
                                                 (__nv_bfloat16*)(base + p.tc_wo), C, A, c.n_heads, pl->head_dim,
                                                 (pl->head_dim + 15) / 16 * 16,
                                                 1.4426950408889634f / sqrtf((float)pl->head_dim));
+      if (p.rope_tab != 0) {   // RoPE (cos, sin) table, once per weight pack instead of once per attention call
+        const int HDP = (pl->head_dim + 15) / 16 * 16;
+        rope_table_kernel<<<(ROPE_TAB_LEN * (HDP / 2) + 255) / 256, 256, 0, st>>>((float2*)(base + p.rope_tab), dst(p.rope), ROPE_TAB_LEN,
+                                                                                 pl->head_dim / 2, HDP / 2);
+      }
     }
   if (c.enc_in_ch > 0) {
     // deconv.weight [C, 2S, 3, 3] -> [9][8][C] (outputs >= 2S stay zero from the memset)
@@ -397,22 +404,26 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
   const int NTL = (L + 127) / 128;
   __nv_bfloat16* qkv = (__nv_bfloat16*)(wsp + ws.qkv_img);
   __nv_bfloat16* oimg = (__nv_bfloat16*)(wsp + ws.o_img);
-  float2* rope = (float2*)(wsp + ws.rope);
+  const float2* rope = (const float2*)(wsp + ws.rope);
   const SeqMap xmap = make_seq_map(axis, d.Tf, d.F, C);
-  if (c.rope) {
-    rope_table_kernel<<<(L * (HDP / 2) + 255) / 256, 256, 0, st>>>(rope, (const float*)(packed + p.rope), L, hd / 2, HDP / 2);
+  int rope_stride = L;
+  if (c.rope && L <= ROPE_TAB_LEN && p.rope_tab != 0) {        // the pack-time table covers this length
+    rope = (const float2*)(packed + p.rope_tab);
+    rope_stride = ROPE_TAB_LEN;
+  } else if (c.rope) {
+    rope_table_kernel<<<(L * (HDP / 2) + 255) / 256, 256, 0, st>>>((float2*)(wsp + ws.rope), (const float*)(packed + p.rope), L, hd / 2, HDP / 2);
     TFL_LAUNCH_CHECK();
   }
   {
     QkvTcParams q;
     q.x = x; q.map = xmap; q.gamma = (const float*)(packed + p.attn_gamma); q.eps = c.eps;
-    q.wimg = packed + p.tc_qkv; q.rope = c.rope ? rope : nullptr; q.qkv = qkv;
+    q.wimg = packed + p.tc_qkv; q.rope = c.rope ? rope : nullptr; q.rope_stride = rope_stride; q.qkv = qkv;
     q.C = C; q.G = c.num_groups; q.L = L; q.NTL = NTL; q.nseq = nseq; q.heads = heads; q.hd = hd; q.HDP = HDP;
     q.NPART = NPART; q.n_tiles = nseq * NTL; q.qscale = 1.4426950408889634f / sqrtf((float)hd);
     const uint32_t smem = 3u * C * NPART * 2 + 3u * C * 256 + C * 4 + 256;
     TFL_CUDA(opt_in_smem(qkv_tc_kernel, smem));
     const int grid = q.n_tiles < pl->sm_count ? q.n_tiles : pl->sm_count;
-    qkv_tc_kernel<<<grid, QKV_THREADS, smem, st>>>(q);
+    TFL_CUDA(launch_pdl(qkv_tc_kernel, dim3(grid), dim3(QKV_THREADS), smem, st, q));
     TFL_LAUNCH_CHECK();
   }
   {
@@ -444,7 +455,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       auto kern = HDP == 16 ? attn_tc2_kernel<1> : attn_tc2_kernel<2>;
       TFL_CUDA(opt_in_smem(kern, smem));
       const int grid = a2.n_items < pl->sm_count ? a2.n_items : pl->sm_count;
-      kern<<<grid, ATT2_THREADS, smem, st>>>(a2);
+      TFL_CUDA(launch_pdl(kern, dim3(grid), dim3(ATT2_THREADS), smem, st, a2));
     }
     TFL_LAUNCH_CHECK();
     // one tail row (frequency axis of n_fft 2048: 1025 = 8 * 128 + 1) has nothing to share between rows and long key
@@ -453,15 +464,15 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
       // warp-level tensor-core path: one warp per (sequence, head), all tail rows at once
       long long blocks = ((long long)nseq * heads + 7) / 8;
       if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
-      if (HDP == 16) attn_tail_mma_kernel<1><<<(int)blocks, 256, 0, st>>>(ap, ap.NQT * 128);
-      else attn_tail_mma_kernel<2><<<(int)blocks, 256, 0, st>>>(ap, ap.NQT * 128);
+      if (HDP == 16) TFL_CUDA(launch_pdl(attn_tail_mma_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, ap, ap.NQT * 128));
+      else TFL_CUDA(launch_pdl(attn_tail_mma_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, st, ap, ap.NQT * 128));
       TFL_LAUNCH_CHECK();
     } else if (tail_q) {
       const long long warps = (long long)nseq * heads * tail_q;
       long long blocks = (warps + 7) / 8;
       if (blocks > (long long)pl->sm_count * 8) blocks = (long long)pl->sm_count * 8;
       TFL_CUDA(opt_in_smem(attn_tail_rows_kernel<1>, tsm));
-      attn_tail_rows_kernel<1><<<(int)blocks, 256, tsm, st>>>(ap, ap.NQT * 128);
+      TFL_CUDA(launch_pdl(attn_tail_rows_kernel<1>, dim3((unsigned)blocks), dim3(256), tsm, st, ap, ap.NQT * 128));
       TFL_LAUNCH_CHECK();
     }
   }
@@ -472,7 +483,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     const uint32_t smem = (uint32_t)NPART * C * 2 + PROJ_STAGES * (uint32_t)NPART * 256 + 2 * PROJ_STG_BYTES + 256;
     TFL_CUDA(opt_in_smem(proj_tc_kernel, smem));
     const int grid = pp.n_tiles < pl->sm_count ? pp.n_tiles : pl->sm_count;
-    proj_tc_kernel<<<grid, 320, smem, st>>>(pp);
+    TFL_CUDA(launch_pdl(proj_tc_kernel, dim3(grid), dim3(320), smem, st, pp));
     TFL_LAUNCH_CHECK();
   }
   return 0;
