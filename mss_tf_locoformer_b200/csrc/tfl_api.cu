@@ -396,7 +396,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
   const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
   const int C = c.emb_dim, hd = pl->head_dim, heads = c.n_heads;
   TFL_CHECK(attn_tc_supported(C, heads, hd),
-            "bf16 tcgen05 attention needs head_dim in {8,16,24,32}, emb_dim %% 16 == 0 and n_heads * head_dim(padded to 16) "
+            "bf16 tcgen05 attention needs an even head_dim <= 32, emb_dim %% 16 == 0 and n_heads * head_dim(padded to 16) "
             "in {32,64,96,128} (got emb_dim %d, n_heads %d, head_dim %d); use precision fp32", C, heads, hd);
   const int HDP = (hd + 15) / 16 * 16, NPART = heads * HDP;
   const int L = axis == TFL_AXIS_FREQ ? d.F : d.Tf;

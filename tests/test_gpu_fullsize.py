@@ -94,6 +94,12 @@ def test_musdb18_small_6s_fp32(pkg):
     _mss_case(pkg, SMALL, bench.SEG, "fp32", 70.0, 1e-4, what="small 3 layers 6 s")
 
 
+def test_musdb18_small_bf16(pkg):
+    """configs/musdb18_small.yaml in bf16 mode: head_dim 12 is zero-padded to 16 for the K = 16 MMA granularity
+    (VERDICT r01 item 7); emb 48 runs the one-CTA FFN kernel (emb_dim % 32 != 0)."""
+    _mss_case(pkg, SMALL, bench.SEG // 2, "bf16", 40.0, what="small 3 layers 3 s")
+
+
 def test_batch8_full_size_rows_independent_bf16(pkg):
     """Batch 8 at full size (the bench shape): every row equals the same segment run alone, bit for bit."""
     model = bench.make_state_dict(dict(bench.VARIANTS["D"])).cuda()
