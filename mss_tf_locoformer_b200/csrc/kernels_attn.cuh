@@ -635,17 +635,13 @@ __global__ void tc_pack_qkv_kernel(const float* __restrict__ wqkv, const float* 
 #define QKV_L2_PREFETCH 1
 #endif
 constexpr int QKV_PF_DIST = 2;
+// (r02, measured with ncu: five warpgroups + setmaxnreg + 32-column tcgen05.ld in the epilogue did not help on the
+// frequency axis, 0.669 vs 0.662 ms, and lost on the time axis, 0.887 vs 0.780 ms -- reverted.)
 constexpr int QKV_PRODUCER_WARPS = 8;
 #ifndef QKV_UF
 #define QKV_UF 8   // (8-row, group) units a producer lane keeps in flight (4: two round trips per tile, r01)
 #endif
-constexpr int QKV_THREADS = 32 * (4 + QKV_PRODUCER_WARPS + 8);
-// Five warpgroups: {loader / L2 prefetcher, MMA lane, two idle warps}, producers x 2, epilogue x 2.  setmaxnreg re-splits the
-// launch allocation (640 x 96): the epilogue warps get 112 registers so that each holds a 32-column tcgen05.ld (4 KB per
-// warp) in flight -- TMEM read-back delivers 64 B/clk per SM, and with 8 x 2 KB in flight it ran latency-bound at about
-// half of that: the read-back of the 192 KB of accumulators per tile, not HBM, paced the kernel (r02).
-constexpr int QKV_REGS_CTRL = 56, QKV_REGS_EPI = 112;
-static_assert(QKV_REGS_CTRL + 2 * 96 + 2 * QKV_REGS_EPI <= 480, "register budget of the CTA");
+constexpr int QKV_THREADS = 32 * (2 + QKV_PRODUCER_WARPS + 8);
 
 __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
   using namespace tc;
@@ -677,7 +673,6 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
   griddep_wait();                                          // (PDL) the prologue overlapped the previous kernel's tail
 
   if (warp == 0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(QKV_REGS_CTRL));
     if (lane == 0) {
       mbar_arrive_expect_tx(BAR(W_FULL), 3 * part_bytes);
       for (int i = 0; i < 3; ++i) bulk_g2s(sbase + off_w + i * part_bytes, p.wimg + (size_t)i * part_bytes, part_bytes, BAR(W_FULL));
@@ -714,7 +709,6 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
     }
 #endif
   } else if (warp == 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(QKV_REGS_CTRL));
     {
       const uint32_t idesc = instr_desc(128, NPART);
       const uint32_t hi = (128u >> 4) | (1u << 14);
@@ -740,12 +734,10 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
         if (++slot == 3) { slot = 0; aph ^= 1; }
       }
     }
-  } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(QKV_REGS_CTRL));   // idle: completes the control warpgroup
-  } else if (warp < 4 + QKV_PRODUCER_WARPS) {
+  } else if (warp < 2 + QKV_PRODUCER_WARPS) {
     // ---- producers: one (row, group) item per thread and pass; the row stays in registers between the
     //      sum-of-squares and the scaling, so x is read exactly once ----
-    const int tp = threadIdx.x - 128;
+    const int tp = threadIdx.x - 64;
     const int G = p.G, D = C / G;
     const float rs = rsqrtf((float)D);
     uint32_t slot = 0, ph = 0;
@@ -761,7 +753,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
         // 16-byte chunk per lane, 8 consecutive rows per chunk column: conflict-free.  The group's sum of squares is
         // two shuffles.  Eight items per thread and tile, four in flight at a time.
         const int r8 = lane >> 2, q4 = lane & 3;
-        const int pw = warp - 4;                              // producer warp 0 .. QKV_PRODUCER_WARPS - 1
+        const int pw = warp - 2;                              // producer warp 0 .. QKV_PRODUCER_WARPS - 1
         // rows at or beyond ceil64(L) are never written to the images (see the epilogue): their A rows are left alone
         const int rows_used = min(128, ((p.L + 63) & ~63) - jt * 128);
         const int n_blk = ((rows_used + 7) >> 3) * G;          // (8-row block, group) units per tile
@@ -869,8 +861,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       if (++slot == 3) { slot = 0; ph ^= 1; }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(QKV_REGS_EPI));
-    const int ew = warp - (4 + QKV_PRODUCER_WARPS);
+    const int ew = warp - (2 + QKV_PRODUCER_WARPS);
     const int e = ew >> 2;                     // column half owned by this group
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
@@ -892,42 +883,31 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
       // nor written -- on the time axis (259 rows in three 128-row tiles) that is 17 % of the image.
       const int row_lim = ((p.L + 63) & ~63) - jt * 128;         // rows of this tile anyone reads
       const bool warp_live = quarter * 32 < row_lim;
-      auto emit16 = [&](const uint32_t* r, int part, int c0) {   // 16 accumulator columns -> RoPE -> two 16-byte stores
-        const int head = c0 / HDP, d0 = c0 - head * HDP;
-        uint32_t w[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
-          if (part < 2) {
-            const float2 f = d0 == 0 ? cs[i >> 1] : cs[8 + (i >> 1)];   // d0 is 0 or 16 (HDP <= 32)
-            const float ra = a * f.x - b * f.y, rb = b * f.x + a * f.y;
-            a = ra; b = rb;
-          }
-          w[i >> 1] = pack_bf16(a, b);
-        }
-        __nv_bfloat16* dst = p.qkv + ((((size_t)part * p.nseq + s) * p.heads + head) * NTL + jt) * tile_elems +
-                             ((size_t)(d0 >> 3) * 128 + m) * 8;
-        if (m < row_lim) {
-          *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(dst + 1024) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-      };
       for (int part = 0; part < 3; ++part) {
         mbar_wait(BAR(D_FULL + part), (uint32_t)(it & 1));
         tc_fence_after();
-        int c0 = col_lo;
-        for (; warp_live && c0 + 32 <= col_hi; c0 += 32) {       // 32 columns (4 KB per warp) per TMEM round trip
-          uint32_t r[32];
-          tmem_ld32(lane_addr + part * NPART + c0, r);
-          tc_wait_ld();
-          emit16(r, part, c0);
-          emit16(r + 16, part, c0 + 16);
-        }
-        for (; warp_live && c0 < col_hi; c0 += 16) {
+        for (int c0 = col_lo; warp_live && c0 < col_hi; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(lane_addr + part * NPART + c0, r);
           tc_wait_ld();
-          emit16(r, part, c0);
+          const int head = c0 / HDP, d0 = c0 - head * HDP;
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
+            if (part < 2) {
+              const float2 f = d0 == 0 ? cs[i >> 1] : cs[8 + (i >> 1)];   // d0 is 0 or 16 (HDP <= 32)
+              const float ra = a * f.x - b * f.y, rb = b * f.x + a * f.y;
+              a = ra; b = rb;
+            }
+            w[i >> 1] = pack_bf16(a, b);
+          }
+          __nv_bfloat16* dst = p.qkv + ((((size_t)part * p.nseq + s) * p.heads + head) * NTL + jt) * tile_elems +
+                               ((size_t)(d0 >> 3) * 128 + m) * 8;
+          if (m < row_lim) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + 1024) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         }
         tc_fence_before();
         mbar_arrive(BAR(D_EMPTY + part));

@@ -32,7 +32,10 @@ struct Ffn2Geom {
   uint32_t a_slot_bytes, g_buf_bytes;
   uint32_t off_a, off_g, off_w, off_tab, off_bar, smem_bytes;
 };
-constexpr int FFN2_NA = 3;             // A-tile slots: the tile being multiplied and two ahead
+#ifndef FFN2_NA_SLOTS
+#define FFN2_NA_SLOTS 3
+#endif
+constexpr int FFN2_NA = FFN2_NA_SLOTS;   // A-tile slots: the tile being multiplied and two ahead
 constexpr int FFN2_THREADS = 640;
 // setmaxnreg budgets per warpgroup: loaders / MMA issuers, A producers, SwiGLU groups (x2), output warps.  setmaxnreg
 // only re-splits what the CTA was given at launch -- 640 threads x 96 registers -- so the five budgets must sum to

@@ -76,9 +76,20 @@ class Engine:
             pass
 
     # ---- weights -------------------------------------------------------------------
+    @staticmethod
+    def _version_of(t: torch.Tensor) -> int:
+        try:
+            return t._version
+        except RuntimeError:          # inference-mode tensors do not track versions: repack on every data_ptr change only
+            return -1
+
+    def invalidate(self):
+        """Force a re-pack at the next forward (after in-place writes the fingerprint cannot see, e.g. ``p.data.copy_``)."""
+        self._fingerprint = None
+
     def ensure_packed(self, params: Dict[str, torch.Tensor]):
         tensors = [params[k] for k in self.keys]
-        fp = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        fp = tuple((t.data_ptr(), self._version_of(t), t.device) for t in tensors)
         if fp == self._fingerprint and self.packed is not None:
             return
         dev = tensors[0].device

@@ -32,8 +32,22 @@ class _SeparatorBase(nn.Module):
     def _ready(self) -> Engine:
         if self._engine is None:
             self._engine = Engine(self._engine_cfg)
-        self._engine.ensure_packed(dict(self.state_dict(keep_vars=True)))
+        refs = getattr(self, "_param_refs", None)
+        if refs is None:            # parameter objects by state_dict key, collected once (not once per forward)
+            refs = dict(self.state_dict(keep_vars=True))
+            self._param_refs = refs
+        self._engine.ensure_packed(refs)
         return self._engine
+
+    def repack(self):
+        """Re-read the parameters into the packed weight image at the next forward.
+
+        The image is refreshed automatically when a parameter's storage or version counter changes (``load_state_dict``,
+        ``.to()``, optimiser steps); call this after writes that bypass the version counter (``p.data.copy_(ema)``) or
+        after replacing a parameter object."""
+        self._param_refs = None
+        if self._engine is not None:
+            self._engine.invalidate()
 
     def _build_blocks(self, n_layers, rope_freq, rope_time, **kw):
         self.blocks = nn.ModuleList([])

@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+V=mss_tf_locoformer_b200/csrc/variants
+for lib in default na2; do
+for ax in 0 1; do
+if [ $lib = default ]; then unset TFL_LIB; else export TFL_LIB=$V/lib_$lib.so; fi
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_ffn_${lib}_$ax.csv python profiles/run_stage.py ffn 8 $ax > /dev/null 2>&1
+echo "$lib axis $ax: $(python profiles/summarize_launches.py gpurun_out/r02_ffn_${lib}_$ax.csv 2>/dev/null | grep ffn_tc2)"
+done; done
+unset TFL_LIB
+for ax in 0 1; do
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_l_attn${ax}_g.csv python profiles/run_stage.py attn 8 $ax > /dev/null 2>&1
+echo "axis $ax:"; python profiles/summarize_launches.py gpurun_out/r02_l_attn${ax}_g.csv 2>/dev/null | sed -n 2,5p
+done
