@@ -89,6 +89,45 @@ inline SeqMap make_seq_map(int axis, int n_frames, int n_freq, int C) {
   return m;
 }
 
+// 128-row tiling of the (sequence, position) rows of one attention call for the q|k|v and head-merge GEMMs.
+//   legacy  : NTL = ceil(L / 128) tiles per sequence, the last one partial;
+//   packed  : when only a few rows spill over a tile boundary (1025 = 8 * 128 + 1, 259 = 2 * 128 + 3) the NTF = L / 128 full
+//             tiles of every sequence come first (tile = s * NTF + jt) and the spill-over rows of ALL sequences are packed
+//             into ceil(nseq * n_tail / 128) tiles behind them -- instead of one nearly empty tile per sequence (a third
+//             of the time-axis tiles of a 6-s segment).
+struct TileMap {
+  int nseq, L, NTL, NTF, n_tail, packed;
+  int n_full;    // nseq * NTF (packed) or nseq * NTL (legacy)
+  int n_tiles;
+  __host__ __device__ __forceinline__ bool locate(int tile, int m, int& s, int& j) const {
+    if (!packed) { s = tile / NTL; j = (tile - s * NTL) * 128 + m; return j < L; }
+    if (tile < n_full) { s = tile / NTF; j = (tile - s * NTF) * 128 + m; return true; }
+    const long long g = (long long)(tile - n_full) * 128 + m;
+    s = (int)(g / n_tail); j = NTF * 128 + (int)(g - (long long)s * n_tail);
+    return s < nseq;
+  }
+  // tile of the attention-output image that holds row j of sequence s, and the row inside it
+  __host__ __device__ __forceinline__ void o_slot(int s, int j, long long& tile, int& row) const {
+    if (!packed) { tile = (long long)s * NTL + (j >> 7); row = j & 127; return; }
+    if (j < NTF * 128) { tile = (long long)s * NTF + (j >> 7); row = j & 127; return; }
+    const long long g = (long long)s * n_tail + (j - NTF * 128);
+    tile = n_full + (g >> 7); row = (int)(g & 127);
+  }
+};
+inline TileMap make_tile_map(int nseq, int L, bool pack_tail) {
+  TileMap t;
+  t.nseq = nseq; t.L = L; t.NTL = (L + 127) / 128; t.NTF = L / 128; t.n_tail = L - t.NTF * 128;
+  t.packed = (pack_tail && t.n_tail > 0 && t.NTF > 0) ? 1 : 0;
+  if (t.packed) {
+    t.n_full = nseq * t.NTF;
+    t.n_tiles = t.n_full + (int)(((long long)nseq * t.n_tail + 127) / 128);
+  } else {
+    t.n_full = nseq * t.NTL;
+    t.n_tiles = t.n_full;
+  }
+  return t;
+}
+
 inline SeqMap make_dense_map(long long seq_stride, long long pos_stride) {
   SeqMap m; m.inner = 1 << 30; m.outer_stride = 0; m.inner_stride = seq_stride; m.pos_stride = pos_stride;
   return m;

@@ -157,3 +157,27 @@ def test_n_fft_4096_bf16(pkg):
                ffn_hidden_dim=[128, 128], conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5)
     _mss_case(pkg, cfg, 9000, "bf16", 40.0, what="n_fft 4096")
     _mss_case(pkg, cfg, 9000, "fp32", 70.0, 1e-4, what="n_fft 4096")
+
+
+@pytest.mark.parametrize("precision,sisdr,maxabs", [("fp32", 70.0, 2e-4), ("bf16", 40.0, None)])
+def test_espnet_whamr_config(pkg, precision, sisdr, maxabs):
+    """SURVEY N3 at the recipe's real size: egs2/whamr/enh1/conf/tuning/train_enh_tflocoformer.yaml:53-80 (n_fft 256 ->
+    F = 129 = 128 + 1 tail bin, 6 layers, emb 128, conv1d_kernel 8, hidden 192, 2 speakers), 4 s at 8 kHz (501 frames),
+    through the ESPnet adapter, against the reference separator (standalone class: the same arithmetic)."""
+    from mss_tf_locoformer_b200.espnet_separator import TFLocoformerSeparator as EspnetSeparator
+    cfg = dict(num_spk=2, n_layers=6, emb_dim=128, norm_type="rmsgroupnorm", num_groups=4, tf_order="ft", n_heads=4,
+               flash_attention=False, attention_dim=128, pos_enc="rope", ffn_type=MAC, ffn_hidden_dim=[192, 192],
+               conv1d_kernel=8, conv1d_shift=1, dropout=0.0, eps=1e-5)
+    torch.manual_seed(11)
+    model = EspnetSeparator(129, **cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(12)
+    x = torch.complex(torch.randn(2, 501, 129, generator=g), torch.randn(2, 501, 129, generator=g))
+    want, kind = _reference_forward("TFLocoformerSeparator", cfg, sd, x)
+    model = model.cuda()
+    model.precision = precision
+    ilens = torch.tensor([501, 501])
+    with torch.no_grad():
+        outs, ol, _ = model(x.cuda(), ilens)
+    assert len(outs) == 2 and ol is ilens
+    _compare(torch.stack(outs, dim=1), want, sisdr, maxabs, f"espnet-whamr[{precision}, vs {kind}]")
