@@ -127,6 +127,43 @@ int tfl_segment_ola(const float* seg_audio, int n_src, int batch, int seg_len, i
 int tfl_pair_stats(const float* est, const float* tgt, int rows, int64_t n, double* out5, double* scratch,
                    size_t scratch_bytes, tfl_stream_t stream);
 
+/* ---- training step: /root/reference/training/train.py:68-172 ------------------------------
+ * fp32 on CUDA cores.  Gradients leave in ONE flat fp32 buffer: one slice per state_dict tensor, in tfl_pack_weights order
+ * and in the reference's own tensor layout, so param.grad of the reference model is the parity target, the data-parallel
+ * all-reduce is one NCCL call on the buffer, and clipping + AdamW are two kernels over it. */
+typedef struct tfl_loss_config {   /* MSSLoss(loss_type='combined'), models/mss_loss.py:18-109 */
+  float si_sdr_weight, l1_weight, spectral_weight, eps;
+  int32_t spec_n_fft, spec_hop;    /* SpectralLoss STFT (2048 / 1024 in the reference, :184-193) */
+} tfl_loss_config;
+/* Returns the flat buffer's length in floats; offsets[i] = start of tensor i's gradient (-1: not trainable, i.e.
+ * attn.rope.freqs), sizes[i] = its element count (both may be NULL). */
+int64_t tfl_train_grad_layout(const tfl_plan* plan, int64_t* offsets, int64_t* sizes, int n_weights);
+size_t tfl_train_workspace_bytes(const tfl_plan* plan, int batch, int n_samples, int spec_n_fft, int spec_hop);
+size_t tfl_train_stage_workspace_bytes(const tfl_plan* plan, int batch, int n_frames, int n_freq);
+/* forward (sub-block inputs saved) -> MSSLoss -> backward.  `weights`: the raw fp32 device tensors tfl_pack_weights took
+ * (the data-gradient GEMMs read qkv.weight / aggregate_heads.weight in place); mixture [B, T]; targets [S, B, T] (mono,
+ * train.py:103-110); grads: flat buffer (overwritten); loss_out[0] = total_loss, then {si_sdr, l1, spectral} per source
+ * (device, 1 + 3 S floats); est_audio (optional) [S, B, T].  Dropout is not applied (p = 0). */
+int tfl_train_forward_backward(const tfl_plan* plan, const void* packed, const float* const* weights, int n_weights,
+                               const float* mixture, const float* targets, int batch, int n_samples,
+                               const tfl_loss_config* loss, float* grads, float* loss_out, float* est_audio,
+                               void* workspace, size_t ws_bytes, tfl_stream_t stream);
+/* Backward of one sub-block (x_out = x_in + branch(x_in)): dx holds dL/dx_out on entry, dL/dx_in on exit; the
+ * sub-block's parameter gradients are accumulated into their slices of `grads`.  models/mss_tflocoformer.py:443-462. */
+int tfl_conv_swiglu_ffn_bwd(const tfl_plan* plan, const void* packed, const float* const* weights, int n_weights, int layer,
+                            int axis, int ffn_index, const float* x_in, float* dx, int batch, int n_frames, int n_freq,
+                            float* grads, void* workspace, size_t ws_bytes, tfl_stream_t stream);
+int tfl_rope_attn_bwd(const tfl_plan* plan, const void* packed, const float* const* weights, int n_weights, int layer,
+                      int axis, const float* x_in, float* dx, int batch, int n_frames, int n_freq, float* grads,
+                      void* workspace, size_t ws_bytes, tfl_stream_t stream);
+/* torch.nn.utils.clip_grad_norm_ (train.py:141): norm_out[0] = total L2 norm, norm_out[1] = min(1, max_norm / (norm + 1e-6))
+ * (device, 2 floats; no host sync).  scratch: >= 592 doubles. */
+int tfl_grad_clip_norm(const float* grads, int64_t n, float max_norm, float* norm_out, double* scratch,
+                       size_t scratch_bytes, tfl_stream_t stream);
+/* torch.optim.AdamW step `step` (1-based) over flat buffers (train.py:351-357); `clip` = norm_out above or NULL. */
+int tfl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* clip,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, tfl_stream_t stream);
+
 /* Every mbarrier wait in the tcgen05 kernels is bounded (~2 s).  A wait that expires is a pipeline protocol error: the
  * kernel records {1, block, thread, shared-memory address of the barrier, parity} in a host-mapped record and traps, so
  * the launch fails loudly (cudaErrorLaunchFailed at the next synchronising call) and every later tfl_* entry point

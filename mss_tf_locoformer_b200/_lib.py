@@ -18,7 +18,12 @@ class TflError(RuntimeError):
 
 _lib = None
 
-_P, _I, _Z, _L = C.c_void_p, C.c_int, C.c_size_t, C.c_int64
+class TflLossConfig(C.Structure):
+    _fields_ = [("si_sdr_weight", C.c_float), ("l1_weight", C.c_float), ("spectral_weight", C.c_float), ("eps", C.c_float),
+                ("spec_n_fft", C.c_int32), ("spec_hop", C.c_int32)]
+
+
+_P, _I, _Z, _L, _F = C.c_void_p, C.c_int, C.c_size_t, C.c_int64, C.c_float
 SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include/tfl.h
     "tfl_version": (_I, []),
     "tfl_last_error": (C.c_char_p, []),
@@ -44,6 +49,14 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_pair_stats": (_I, [_P, _P, _I, _L, _P, _P, _Z, _P]),
     "tfl_bs_band_split": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tfl_bs_band_decode": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "tfl_train_grad_layout": (_L, [_P, C.POINTER(_L), C.POINTER(_L), _I]),
+    "tfl_train_workspace_bytes": (_Z, [_P, _I, _I, _I, _I]),
+    "tfl_train_stage_workspace_bytes": (_Z, [_P, _I, _I, _I]),
+    "tfl_train_forward_backward": (_I, [_P, _P, C.POINTER(_P), _I, _P, _P, _I, _I, C.POINTER(TflLossConfig), _P, _P, _P, _P, _Z, _P]),
+    "tfl_conv_swiglu_ffn_bwd": (_I, [_P, _P, C.POINTER(_P), _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    "tfl_rope_attn_bwd": (_I, [_P, _P, C.POINTER(_P), _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    "tfl_grad_clip_norm": (_I, [_P, _L, _F, _P, _P, _Z, _P]),
+    "tfl_adamw_step": (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),
     "tfl_debug_set_option": (_I, [_I, _I]),
     "tfl_debug_set_trace": (_I, [_P]),
     "tfl_debug_timeout": (_I, [C.POINTER(C.c_uint32), _I]),

@@ -596,6 +596,7 @@ struct QkvTcParams {
   int C, G, L, NTL, nseq, heads, hd, HDP, NPART;
   int n_tiles;
   float qscale;
+  int pad_to;                       // image rows are produced up to ceil_pad_to(L): 16 (attn_tc2 / tail kernels) or 64 (attn_tc_kernel)
 };
 
 __global__ void rope_table_kernel(float2* __restrict__ tab, const float* __restrict__ freqs, int L, int half, int half_pad) {
@@ -754,8 +755,8 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
         // two shuffles.  Eight items per thread and tile, four in flight at a time.
         const int r8 = lane >> 2, q4 = lane & 3;
         const int pw = warp - 2;                              // producer warp 0 .. QKV_PRODUCER_WARPS - 1
-        // rows at or beyond ceil64(L) are never written to the images (see the epilogue): their A rows are left alone
-        const int rows_used = min(128, ((p.L + 63) & ~63) - jt * 128);
+        // rows at or beyond ceil_pad_to(L) are never written to the images (see the epilogue): their A rows are left alone
+        const int rows_used = min(128, (p.L + p.pad_to - 1) / p.pad_to * p.pad_to - jt * 128);
         const int n_blk = ((rows_used + 7) >> 3) * G;          // (8-row block, group) units per tile
         // QKV_UF units (2 x 128-bit loads each) in flight per lane: the producers are bound by global-load latency
         // (ncu: the epilogue warps wait on D_FULL, the MMA warp on A_FULL), so a whole tile -- 64 units for 4 groups --
@@ -878,10 +879,10 @@ __global__ void __launch_bounds__(QKV_THREADS, 1) qkv_tc_kernel(QkvTcParams p) {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         cs[i] = (p.rope != nullptr && i < halfp) ? __ldg(&p.rope[(size_t)i * p.rope_stride + j]) : make_float2(1.f, 0.f);
-      // Rows at or beyond ceil64(L) are never read by the attention kernels (attn_tc_kernel masks whole 64-key units,
-      // attn_tc2_kernel ends on a ceil16 block, the tail-row kernel reads single query rows): neither loaded from TMEM
-      // nor written -- on the time axis (259 rows in three 128-row tiles) that is 17 % of the image.
-      const int row_lim = ((p.L + 63) & ~63) - jt * 128;         // rows of this tile anyone reads
+      // Rows at or beyond ceil_pad_to(L) are never read by the attention kernels (attn_tc_kernel masks whole 64-key
+      // units, attn_tc2_kernel and attn_tail_mma_kernel end on a ceil16 block, attn_tail_rows_kernel reads keys < L):
+      // neither loaded from TMEM nor written -- on the time axis (259 rows in three 128-row tiles) that is 29 % of the image.
+      const int row_lim = (p.L + p.pad_to - 1) / p.pad_to * p.pad_to - jt * 128;   // rows of this tile anyone reads
       const bool warp_live = quarter * 32 < row_lim;
       for (int part = 0; part < 3; ++part) {
         mbar_wait(BAR(D_FULL + part), (uint32_t)(it & 1));

@@ -551,7 +551,8 @@ __global__ void __launch_bounds__(256) tap_gemm_kernel(TapGemm p, Epi epi) {
 template <int HD>
 __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                        const float* __restrict__ v, float* __restrict__ o,
-                                                       int L, int hd, int heads, float scale) {
+                                                       int L, int hd, int heads, float scale,
+                                                       float* __restrict__ lse /* [nseq][heads][L] or nullptr (training) */) {
   constexpr int TK = 64, CH = 16;
   __shared__ float ks[TK][HD], vs[TK][HD];
   const int head = blockIdx.y, s = blockIdx.z;
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
     float* dst = o + ((size_t)s * L + i) * ((size_t)heads * hd) + (size_t)head * hd;
 #pragma unroll
     for (int d = 0; d < HD; ++d) if (d < hd) dst[d] = acc[d] * inv;
+    if (lse != nullptr) lse[((size_t)s * heads + head) * L + i] = mx + logf(l);
   }
 }
 

@@ -15,6 +15,7 @@
 #include "kernels_attn.cuh"
 #include "kernels_attn2.cuh"
 #include "kernels_bs.cuh"
+#include "kernels_bwd.cuh"
 
 namespace tfl {
 
@@ -356,8 +357,10 @@ static int ffn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, 
   return gemm_launch(g2, EpiResidual{x, xmap}, st);
 }
 
+// lse != nullptr (training): the log-sum-exp of every (sequence, head, query) is kept and the head-merge projection +
+// residual are skipped when `forward_only_to_o` (the backward pass recomputes q|k|v and o from the saved input).
 static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis, float* x, Dims d,
-                    const Workspace& ws, char* wsp, cudaStream_t st) {
+                    const Workspace& ws, char* wsp, cudaStream_t st, float* lse = nullptr, bool forward_only_to_o = false) {
   NvtxRange nvtx_range("tfl::rope_attn[fp32]");
   const tfl_config& c = pl->cfg;
   const PathPack& p = pl->lay.paths[(size_t)layer * 2 + axis];
@@ -376,10 +379,11 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
   const size_t per = (size_t)nseq * heads * L * hd;
   const float scale = 1.0f / sqrtf((float)hd);
   dim3 grid((L + 127) / 128, heads, nseq);
-#define ATT_CASE(HD) attn_f32_kernel<HD><<<grid, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale)
+#define ATT_CASE(HD) attn_f32_kernel<HD><<<grid, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse)
   if (hd <= 8) ATT_CASE(8); else if (hd <= 16) ATT_CASE(16); else if (hd <= 32) ATT_CASE(32); else ATT_CASE(64);
 #undef ATT_CASE
   TFL_LAUNCH_CHECK();
+  if (forward_only_to_o) return 0;
   TapGemm g2{o, make_dense_map((long long)L * A, A), L, L, 0, 1, A, (const float*)(packed + p.wo), nullptr, C,
              (long long)nseq * L};
   return gemm_launch(g2, EpiResidual{x, xmap}, st);
@@ -419,7 +423,7 @@ static int attn_bf16(const tfl_plan* pl, const char* packed, int layer, int axis
     q.x = x; q.map = xmap; q.gamma = (const float*)(packed + p.attn_gamma); q.eps = c.eps;
     q.wimg = packed + p.tc_qkv; q.rope = c.rope ? rope : nullptr; q.rope_stride = rope_stride; q.qkv = qkv;
     q.C = C; q.G = c.num_groups; q.L = L; q.NTL = NTL; q.nseq = nseq; q.heads = heads; q.hd = hd; q.HDP = HDP;
-    q.NPART = NPART; q.n_tiles = nseq * NTL; q.qscale = 1.4426950408889634f / sqrtf((float)hd);
+    q.NPART = NPART; q.n_tiles = nseq * NTL; q.pad_to = tfl_option(TFL_OPT_ATTN_KERNEL) == 1 ? 64 : 16; q.qscale = 1.4426950408889634f / sqrtf((float)hd);
     const uint32_t smem = 3u * C * NPART * 2 + 3u * C * 256 + C * 4 + 256;
     TFL_CUDA(opt_in_smem(qkv_tc_kernel, smem));
     const int grid = q.n_tiles < pl->sm_count ? q.n_tiles : pl->sm_count;
@@ -862,3 +866,5 @@ int tfl_tc_selftest(const float* A, const float* B, float* D, void* scratch, int
 }
 
 }  // extern "C"
+
+#include "tfl_train.cuh"

@@ -130,7 +130,9 @@ def test_real_width_one_layer_bf16(pkg, name, cfg, n_samples):
 
 @pytest.mark.parametrize("name,cfg,shape", [("golden32", None, None), ("D", VARIANT_D, (1, 5, 300)),
                                             ("Y", VARIANT_Y, (2, 7, 131)), ("D_long", VARIANT_D, (1, 3, 1025)),
-                                            ("D_time", VARIANT_D, (1, 259, 6))])
+                                            ("D_time", VARIANT_D, (1, 259, 6)),
+                                            ("D_time_spill3", VARIANT_D, (1, 259, 100)),     # 100 sequences x 3 tail rows
+                                            ("D_freq_spill2", VARIANT_D, (1, 150, 1025))])   # 150 sequences x 1 tail row
 def test_attention_tc_vs_oracle(pkg, name, cfg, shape):
     """tcgen05 attention (S = QK^T and P.V on the tensor core, exp2 softmax) on both axes."""
     if cfg is None:
