@@ -291,6 +291,140 @@ def run_bs(args, dev):
         "gpu_launches": int(lib.tfl_launch_count() - n0)}))
 
 
+# BASELINE config 5: configs/musdb18_rtx5090_xlarge.yaml:22-44 (dropout forced to 0: SURVEY 8d), 15-s samples, batch 1 per GPU
+TRAIN_CFGS = {
+    "xlarge": (dict(n_fft=4096, hop_length=1024, n_sources=4, n_layers=12, emb_dim=256, norm_type="rmsgroupnorm",
+                    num_groups=8, tf_order="ft", n_heads=16, flash_attention=True, attention_dim=256, pos_enc="rope",
+                    ffn_type=MAC, ffn_hidden_dim=[1024, 1024], conv1d_kernel=4, conv1d_shift=1, dropout=0.0, eps=1e-5),
+               661500, "musdb18_rtx5090_xlarge.yaml training step (12 layers, emb 256, n_fft 4096, 15-s samples)"),
+    "D": (VARIANT_D, SEG, "musdb18 Variant D training step (6 layers, emb 128, n_fft 2048, 6-s samples)"),
+}
+
+
+def time_reference_gpu_train(cfg, sd, dev, mix, tgt, steps, loss_w):
+    """The unmodified reference model + MSSLoss + clip + torch AdamW, eager on this GPU under bf16 autocast
+    (training/train.py:115-146 with amp_dtype bfloat16).  -> dict or a reason string."""
+    from oracle import build_ref
+    if not build_ref.available():
+        return "oracle/_ref not staged"
+    try:
+        ref, _ = reference_model(dict(cfg, flash_attention=True), sd, dev)
+        from models.mss_loss import MSSLoss
+        ref.train()
+        crit = MSSLoss(loss_type="combined", si_sdr_weight=loss_w[0], l1_weight=loss_w[1], spectral_weight=loss_w[2])
+        opt = torch.optim.AdamW([p for p in ref.parameters() if p.requires_grad], lr=3e-4, weight_decay=0.01, eps=1e-8)
+        names = ["vocals", "drums", "bass", "other"]
+        targets = {n: tgt[i] for i, n in enumerate(names)}
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = crit(ref(mix), targets)["total_loss"]
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=5.0)
+            opt.step()
+            return loss
+        one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        peak = torch.cuda.max_memory_allocated() / 2 ** 30
+        del ref, opt
+        torch.cuda.empty_cache()
+        return {"ms_per_step": ms, "value": mix.shape[0] * mix.shape[1] / SR / (ms / 1e3), "unit": "audio-s/s",
+                "peak_gib": round(peak, 1), "mode": "bf16 autocast, flash attention, eager autograd, torch AdamW",
+                "what": "unmodified reference TFLocoformerMSS + MSSLoss training step, PyTorch eager on this GPU"}
+    except RuntimeError as e:   # out of memory at this size is a finding, not a failure of the bench
+        torch.cuda.empty_cache()
+        return "failed: " + str(e).splitlines()[0][:160]
+
+
+def run_train(args, dev, rank, world):
+    """BASELINE config 5: one data-parallel training step per `step` (forward, MSSLoss, backward, NCCL gradient average,
+    clip, AdamW) through mss_tf_locoformer_b200.training.Trainer; every rank trains on its own sample(s)."""
+    import torch.distributed as dist
+    import mss_tf_locoformer_b200 as pkg
+    from mss_tf_locoformer_b200 import _lib
+    from mss_tf_locoformer_b200.training import Trainer
+    cfg, n_samples, what = TRAIN_CFGS[args.train]
+    if args.train_seconds > 0:
+        n_samples = int(args.train_seconds * SR)
+    B = args.train_batch
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    torch.manual_seed(0)
+    model = pkg.TFLocoformerMSS(**cfg).to(dev)
+    loss_w = (1.0, 0.1, 0.15)                       # musdb18_rtx5090_xlarge.yaml:47-52
+    tr = Trainer(model, lr=3e-4, weight_decay=0.01, si_sdr_weight=loss_w[0], l1_weight=loss_w[1], spectral_weight=loss_w[2])
+    mix_host = make_mixture(B, n_samples, seed=1234 + rank).pin_memory()
+    g = torch.Generator().manual_seed(77 + rank)
+    tgt_host = (0.25 * mix_host[None] + 0.05 * torch.randn(4, B, n_samples, generator=g)).pin_memory()
+    mix, tgt = mix_host.to(dev), tgt_host.to(dev)
+    losses = []
+    for _ in range(args.warmup):
+        losses.append(tr.step(mix, tgt)[0:1].clone())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = lib.tfl_launch_count()
+    sampler = ClockSampler(dev.index or 0)
+    with sampler:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            losses.append(tr.step(mix, tgt)[0:1].clone())
+        e1.record()
+        torch.cuda.synchronize()
+    launches = int(lib.tfl_launch_count() - n0)
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    # e2e: the step from pinned host memory, loss read back
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(max(1, args.steps // 2)):
+        loss = tr.step(mix_host.to(dev, non_blocking=True), tgt_host.to(dev, non_blocking=True))
+        loss_host = loss.cpu()
+    e3.record()
+    torch.cuda.synchronize()
+    ms_e2e = torch.tensor([e2.elapsed_time(e3) / max(1, args.steps // 2)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms, ms_e2e = float(ms), float(ms_e2e)
+    secs = B * n_samples / SR
+    fl = algorithmic_flops(cfg, B, n_samples)
+    ref = None
+    if args.reference_gpu:
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        ref = time_reference_gpu_train(cfg, sd, dev, mix, tgt, max(1, args.steps // 2), loss_w)
+    ls = [float(x) for x in torch.cat(losses).cpu()]
+    print(json.dumps({
+        "metric": "trained audio-sec/sec (forward + loss + backward + gradient all-reduce + clip + AdamW)",
+        "value": world * secs / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": what, "batch_per_gpu": B, "seconds_per_sample": n_samples / SR, "parallelism": f"dp{world}",
+                   "loss": "MSSLoss combined (si_sdr 1.0, l1 0.1, spectral 0.15)", "optimizer": "AdamW lr 3e-4 wd 0.01, clip 5.0",
+                   "params": int(sum(p.numel() for p in model.parameters() if p.requires_grad)),
+                   "grad_allreduce_bytes": int(tr.total * 4) if world > 1 else 0},
+        "e2e": {"value": world * secs / (ms_e2e / 1e3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(mix_host.numel() * 4 + tgt_host.numel() * 4), "d2h_bytes_per_step": int(loss_host.numel() * 4)},
+        "algorithmic_tflops_per_step": 3 * fl["total"] / 1e12,
+        "achieved_tflops": 3 * fl["total"] / 1e12 / (ms / 1e3),
+        "loss_first_last": [ls[0], ls[-1]], "gpu_launches": launches, "clocks": sampler.summary(),
+        "workspace_gib": round(tr._ws.numel() / 2 ** 30, 1), "reference_gpu_train": ref}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -307,8 +441,12 @@ def main():
     ap.add_argument("--track", type=float, default=0.0,
                     help="BASELINE config 3: separate ONE synthetic track of this many seconds, 6-s segments at 50 %% overlap "
                          "sharded over the ranks (strong scaling); prints its own JSON line")
+    ap.add_argument("--train", default=None, choices=sorted(TRAIN_CFGS),
+                    help="BASELINE config 5: time data-parallel TRAINING steps of this configuration instead of inference")
+    ap.add_argument("--train-seconds", type=float, default=0.0, help="seconds of audio per training sample (0 = the configuration's own)")
+    ap.add_argument("--train-batch", type=int, default=1, help="training samples per GPU per step")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.warmup = max(args.warmup, 3) if (args.impl == "b200" and args.train is None) else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -329,6 +467,9 @@ def main():
     if args.model == "bs":
         if rank == 0:
             run_bs(args, dev)
+        return
+    if args.train is not None:
+        run_train(args, dev, rank, world)
         return
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)

@@ -21,6 +21,9 @@ namespace tfl {
 // ---- tap-GEMM epilogues of the backward pass -------------------------------------------------------------------------
 struct EpiStoreDense {  // out[r][n] = v
   float* out;
+  __device__ __forceinline__ void pair(int s, int j, long long r, int n, int N, float v0, float v1) const {
+    if (n < N) *reinterpret_cast<float2*>(out + r * N + n) = make_float2(v0, v1);
+  }
   __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
     float* dst = out + r * N + n0;
     if (n0 + 8 <= N) {
@@ -32,6 +35,9 @@ struct EpiStoreDense {  // out[r][n] = v
 
 struct EpiStoreMap {  // out[s, j, n] = v (rows addressed through a SeqMap, e.g. the channels-last residual layout)
   float* out; SeqMap omap;
+  __device__ __forceinline__ void pair(int s, int j, long long r, int n, int N, float v0, float v1) const {
+    if (n < N) *reinterpret_cast<float2*>(out + omap.base(s) + (long long)j * omap.pos_stride + n) = make_float2(v0, v1);
+  }
   __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
     float* dst = out + omap.base(s) + (long long)j * omap.pos_stride + n0;
     if (n0 + 8 <= N) {
@@ -46,6 +52,14 @@ struct EpiStoreMap {  // out[s, j, n] = v (rows addressed through a SeqMap, e.g.
 //   dh[r][2h] = dG * silu(gate),  dh[r][2h+1] = dG * value * silu'(gate)      (models/mss_tflocoformer.py:648-649)
 struct EpiSwiGLUBwd {
   const float* dg; float* hid; float* dh; int H;
+  __device__ __forceinline__ void pair(int s, int j, long long r, int n, int N, float v0, float v1) const {
+    if (n >= N) return;
+    const float sig = 1.f / (1.f + expf(-v1));
+    const float silu = v1 * sig;
+    const float d = dg[r * H + (n >> 1)];
+    hid[r * H + (n >> 1)] = v0 * silu;
+    *reinterpret_cast<float2*>(dh + r * N + n) = make_float2(d * silu, d * v0 * (sig * (1.f + v1 * (1.f - sig))));
+  }
   __device__ __forceinline__ void operator()(int s, int j, long long r, int n0, int N, const float* v) const {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

@@ -419,6 +419,9 @@ struct EpiSwiGLU {  // columns are (value, gate) interleaved; writes hid[r][n/2]
     float* dst = hid + r * H + (n0 >> 1);
     if (n0 + 8 <= N) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
     else for (int i = 0; i < 4; ++i) if (n0 + 2 * i < N) dst[i] = o[i];
+  }  // two adjacent columns (n even): the (value, gate) pair of one hidden channel -- the tf32 MMA kernel's epilogue unit
+  __device__ __forceinline__ void pair(int s, int j, long long r, int n, int N, float v0, float v1) const {
+    if (n < N) hid[r * H + (n >> 1)] = v0 * (v1 / (1.f + expf(-v1)));
   }
 };
 
@@ -432,6 +435,12 @@ struct EpiResidual {  // x[s, j, n] += v   (:447, :456, :462)
       b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
       *reinterpret_cast<float4*>(dst) = a; *reinterpret_cast<float4*>(dst + 4) = b;
     } else for (int i = 0; i < 8; ++i) if (n0 + i < N) dst[i] += v[i];
+  }  __device__ __forceinline__ void pair(int s, int j, long long r, int n, int N, float v0, float v1) const {
+    if (n >= N) return;
+    float2* dst = reinterpret_cast<float2*>(x + omap.base(s) + (long long)j * omap.pos_stride + n);
+    float2 a = *dst;
+    a.x += v0; a.y += v1;
+    *dst = a;
   }
 };
 
@@ -454,6 +463,17 @@ struct EpiQkvRope {  // n -> (which, head, d); RoPE on q,k (interleaved pairs); 
       float* dst = qkv + ((((size_t)which * nseq + s) * heads + head) * L + j) * hd + d;
       *reinterpret_cast<float2*>(dst) = make_float2(a, b);
     }
+  }  __device__ __forceinline__ void pair(int s, int j, long long r, int n, int N, float v0, float v1) const {
+    if (n >= N) return;
+    const int which = n / A, rem = n - which * A, head = rem / hd, d = rem - head * hd;
+    float a = v0, b = v1;
+    if (freqs != nullptr && which < 2) {
+      float sn, cs;
+      sincosf((float)j * __ldg(&freqs[d >> 1]), &sn, &cs);
+      const float ra = a * cs - b * sn, rb = b * cs + a * sn;
+      a = ra; b = rb;
+    }
+    *reinterpret_cast<float2*>(qkv + ((((size_t)which * nseq + s) * heads + head) * L + j) * hd + d) = make_float2(a, b);
   }
 };
 

@@ -16,11 +16,12 @@
 #include "kernels_attn2.cuh"
 #include "kernels_bs.cuh"
 #include "kernels_bwd.cuh"
+#include "kernels_mma.cuh"
 
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {0}, {0}, {0}};   // tfl_debug_set_option
+static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {1}, {0}, {0}};   // tfl_debug_set_option
 int tfl_option(int key) { return g_options[key].load(std::memory_order_relaxed); }
 std::atomic<unsigned long long> g_launches{0};
 
@@ -325,11 +326,16 @@ static int norm_launch(const float* x, float* y, long long rows, int C, int G, c
   return 0;
 }
 
+// Set (per thread, for the duration of a call) by the training entry points when tf32 tensor-core GEMMs are selected
+// (tfl_train.cuh); the inference / parity path never sets it: TFL_PRECISION_FP32 stays exact fp32 on CUDA cores.
+static thread_local bool g_gemm_tf32 = false;
+
 template <class Epi>
 static int gemm_launch(const TapGemm& g, const Epi& epi, cudaStream_t st) {
   TFL_CHECK(g.Kc % GBK == 0 && g.N % 4 == 0, "tap-GEMM needs Kc %% 8 == 0 and N %% 4 == 0 (Kc %d N %d)", g.Kc, g.N);
   dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
-  tap_gemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
+  if (g_gemm_tf32) tap_gemm_mma_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
+  else tap_gemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
   TFL_LAUNCH_CHECK();
   return 0;
 }

@@ -123,7 +123,8 @@ static int wgrad_launch(TapWgrad g, int sm_count, cudaStream_t st) {
   if (splits > 65535) splits = 65535;
   g.rows_per_split = ((g.R + splits - 1) / splits + GBK - 1) / GBK * GBK;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
-  tap_wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
+  if (g_gemm_tf32) tap_wgrad_mma_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
+  else tap_wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   TFL_LAUNCH_CHECK();
   return 0;
 }
@@ -312,6 +313,12 @@ static std::vector<SubBlock> sub_blocks(const tfl_plan* pl) {
   return v;
 }
 
+struct Tf32Scope {   // GEMM arithmetic of one training call: TFL_OPT_TRAIN_TF32 (default on), restored on exit
+  bool prev;
+  Tf32Scope() : prev(g_gemm_tf32) { g_gemm_tf32 = tfl_option(TFL_OPT_TRAIN_TF32) != 0; }
+  ~Tf32Scope() { g_gemm_tf32 = prev; }
+};
+
 static int check_train(const tfl_plan* pl, const void* packed, const float* const* w, int n_weights) {
   TFL_CHECK(pl && packed && w, "null argument");
   TFL_CHECK(n_weights == tfl_num_weight_tensors(pl), "expected %d weight tensors, got %d", tfl_num_weight_tensors(pl), n_weights);
@@ -351,6 +358,7 @@ size_t tfl_train_stage_workspace_bytes(const tfl_plan* pl, int B, int Tf, int F)
 int tfl_conv_swiglu_ffn_bwd(const tfl_plan* pl, const void* packed, const float* const* w, int n_weights, int layer, int axis,
                             int ffn_index, const float* x_in, float* dx, int B, int Tf, int F, float* grads,
                             void* workspace, size_t ws_bytes, tfl_stream_t stream) {
+  Tf32Scope tf32_scope;
   if (check_train(pl, packed, w, n_weights)) return -1;
   TFL_CHECK(x_in && dx && grads && workspace, "null argument");
   TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1) && ffn_index >= 0 && ffn_index < pl->n_ffn,
@@ -367,6 +375,7 @@ int tfl_conv_swiglu_ffn_bwd(const tfl_plan* pl, const void* packed, const float*
 int tfl_rope_attn_bwd(const tfl_plan* pl, const void* packed, const float* const* w, int n_weights, int layer, int axis,
                       const float* x_in, float* dx, int B, int Tf, int F, float* grads, void* workspace, size_t ws_bytes,
                       tfl_stream_t stream) {
+  Tf32Scope tf32_scope;
   if (check_train(pl, packed, w, n_weights)) return -1;
   TFL_CHECK(x_in && dx && grads && workspace, "null argument");
   TFL_CHECK(layer >= 0 && layer < pl->cfg.n_layers && (axis == 0 || axis == 1), "bad layer / axis");
@@ -389,6 +398,7 @@ int tfl_train_forward_backward(const tfl_plan* pl, const void* packed, const flo
                                float* grads, float* loss_out, float* est_audio, void* workspace, size_t ws_bytes,
                                tfl_stream_t stream) {
   NvtxRange nvtx_range("tfl::train_forward_backward");
+  Tf32Scope tf32_scope;
   if (check_train(pl, packed, w, n_weights)) return -1;
   TFL_CHECK(mixture && targets && loss && grads && loss_out && workspace, "null argument");
   const tfl_config& c = pl->cfg;
