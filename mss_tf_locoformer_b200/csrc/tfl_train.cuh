@@ -121,7 +121,7 @@ static int wgrad_launch(TapWgrad g, int sm_count, cudaStream_t st) {
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
-  g.rows_per_split = ((g.R + splits - 1) / splits + GBK - 1) / GBK * GBK;
+  g.rows_per_split = ((g.R + splits - 1) / splits + MMA_BK - 1) / MMA_BK * MMA_BK;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
   if (g_gemm_tf32) tap_wgrad_mma_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   else tap_wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
