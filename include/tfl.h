@@ -189,11 +189,13 @@ int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan,
  *   TFL_OPT_TAIL_KERNEL  1 = attn_tail_rows_kernel (CUDA cores), 2 = attn_tail_mma_kernel (mma.sync; default)
  *   TFL_OPT_PDL          1 = programmatic dependent launch of the bf16 kernels of a step, 0 = plain launches (default:
  *                        measured neutral, 97.8 vs 97.8 ms per step -- the persistent kernels leave no SM free to start on)
- *   TFL_OPT_TRAIN_TF32   GEMMs of the training entry points: 1 = mma.sync tf32 operands, fp32 accumulation (default; the
- *                        reference trains with `tf32: true` under bf16 autocast), 0 = exact fp32 on CUDA cores (parity mode)
+ *   TFL_OPT_TRAIN_MODE   arithmetic of the training entry points: 0 = exact fp32 on CUDA cores (gradient-parity mode);
+ *                        1 = every GEMM as mma.sync tf32 operands with fp32 accumulation; 2 (default) = 1 + the FORWARD
+ *                        pass of the sub-blocks on the bf16 tcgen05 kernels of the inference path (the reference trains
+ *                        with `tf32: true` under bf16 autocast); the backward pass recomputes on the tf32 path
  *   TFL_OPT_TRACE_BASE   first chunk / tile index the pipeline trace records (64 entries per event; default 0) */
 enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_TRACE_BASE = 2, TFL_OPT_TAIL_KERNEL = 3, TFL_OPT_PDL = 4,
-       TFL_OPT_TRAIN_TF32 = 5, TFL_OPT_COUNT = 8 };
+       TFL_OPT_TRAIN_MODE = 5, TFL_OPT_COUNT = 8 };
 int tfl_debug_set_option(int key, int value);
 
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN

@@ -21,7 +21,7 @@
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {1}, {0}, {0}};   // tfl_debug_set_option
+static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {2}, {0}, {0}};   // tfl_debug_set_option
 int tfl_option(int key) { return g_options[key].load(std::memory_order_relaxed); }
 std::atomic<unsigned long long> g_launches{0};
 

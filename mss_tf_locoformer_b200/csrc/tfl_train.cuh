@@ -52,6 +52,8 @@ static int path_weight_index(const tfl_plan* pl, int layer, int axis) {
 
 struct TrainWs {
   Workspace fwd;             // the fp32 inference workspace sits at offset 0
+  Workspace fwd16;           // bf16 workspace of the tcgen05 forward kernels (mixed mode), based at fwd16_base (0 = none)
+  size_t fwd16_base;
   size_t ckpt, dx, dxn, scratch, lse, dbuf, nat, wt, dest, audio, daudio;
   size_t s5, stats_scratch, coef, loss_rows, l1_rows, spec_rows, ltab_tw, ltab_win, lspec_e, lspec_t, lframes, enc_sums;
   size_t total;
@@ -72,7 +74,12 @@ static TrainWs plan_train_ws(const tfl_plan* pl, int B, int Tf, int F, int T, in
   const size_t C = c.emb_dim, A = c.attention_dim, K = c.conv_kernel, S = c.n_src;
   const size_t Hmax = c.ffn_hidden0 > c.ffn_hidden1 ? c.ffn_hidden0 : c.ffn_hidden1;
   w.n_sub = T > 0 ? c.n_layers * 2 * (pl->n_ffn + 1) : 0;
-  w.ckpt = take((size_t)w.n_sub * N * C * sizeof(float));
+  w.ckpt = take((size_t)(w.n_sub > 0 ? w.n_sub + 1 : 0) * N * C * sizeof(float));   // x_0 .. x_n_sub (the residual stream itself)
+  w.fwd16_base = 0;
+  if (T > 0 && attn_tc_supported((int)C, c.n_heads, pl->head_dim)) {
+    w.fwd16 = plan_workspace(pl, B, Tf, F, TFL_PRECISION_BF16);
+    w.fwd16_base = take(w.fwd16.total);
+  }
   w.dx = take(N * C * sizeof(float));
   w.dxn = take(N * C * sizeof(float));
   const size_t rows_f = (size_t)B * Tf * (F + K - 1), rows_t = (size_t)B * F * (Tf + K - 1);
@@ -313,9 +320,9 @@ static std::vector<SubBlock> sub_blocks(const tfl_plan* pl) {
   return v;
 }
 
-struct Tf32Scope {   // GEMM arithmetic of one training call: TFL_OPT_TRAIN_TF32 (default on), restored on exit
+struct Tf32Scope {   // GEMM arithmetic of one training call: TFL_OPT_TRAIN_MODE >= 1 selects tf32 MMAs; restored on exit
   bool prev;
-  Tf32Scope() : prev(g_gemm_tf32) { g_gemm_tf32 = tfl_option(TFL_OPT_TRAIN_TF32) != 0; }
+  Tf32Scope() : prev(g_gemm_tf32) { g_gemm_tf32 = tfl_option(TFL_OPT_TRAIN_MODE) != 0; }
   ~Tf32Scope() { g_gemm_tf32 = prev; }
 };
 
@@ -420,7 +427,6 @@ int tfl_train_forward_backward(const tfl_plan* pl, const void* packed, const flo
   const GradLayout gl = grad_layout(pl);
   const size_t N = (size_t)B * Tf * F, act_bytes = N * C * sizeof(float);
   float* spec = (float*)(wsp + tw.fwd.spec);
-  float* x = (float*)(wsp + tw.fwd.x);
   float* est = (float*)(wsp + tw.fwd.est);
   float* audio = (float*)(wsp + tw.audio);
   float* daudio = (float*)(wsp + tw.daudio);
@@ -430,16 +436,38 @@ int tfl_train_forward_backward(const tfl_plan* pl, const void* packed, const flo
   TFL_CUDA(cudaMemsetAsync(grads, 0, (size_t)gl.total * sizeof(float), st));
 
   // ---------------- forward ----------------
+  // The residual stream is kept: x_k = input of sub-block k lives in checkpoint slot k (x_0 = encoder output, x_n_sub =
+  // decoder input).  Mixed mode (TFL_OPT_TRAIN_MODE 2, the reference's bf16-autocast forward): sub-blocks the tcgen05
+  // kernels cover run on them -- the fused FFN kernel writes slot k + 1 straight from slot k --, the rest and the whole
+  // backward pass stay on the tf32 / fp32 GEMM path.
+  const bool mixed = tfl_option(TFL_OPT_TRAIN_MODE) >= 2;
+  const int enc_prec = mixed ? TFL_PRECISION_BF16 : TFL_PRECISION_FP32;
+  auto slot = [&](size_t k) { return (float*)(wsp + tw.ckpt + k * act_bytes); };
   if (tfl_stft(pl, packed, mixture, B, T, spec, stream)) return -1;
-  if (enc_conv_gln_any(pl, packed, spec, B, Tf, F, x, workspace, ws_bytes, TFL_PRECISION_FP32, stream)) return -1;
+  if (enc_conv_gln_any(pl, packed, spec, B, Tf, F, slot(0), workspace, ws_bytes, enc_prec, stream)) return -1;
   const std::vector<SubBlock> subs = sub_blocks(pl);
   for (size_t k = 0; k < subs.size(); ++k) {
-    TFL_CUDA(cudaMemcpyAsync(wsp + tw.ckpt + k * act_bytes, x, act_bytes, cudaMemcpyDeviceToDevice, st));
     const SubBlock& sb = subs[k];
-    if (sb.kind == 2) { if (attn_f32(pl, pk, sb.layer, sb.axis, x, d, tw.fwd, wsp, st)) return -1; }
-    else if (ffn_f32(pl, pk, sb.layer, sb.axis, sb.kind, x, d, tw.fwd, wsp, st)) return -1;
+    float* x_in = slot(k);
+    float* x_out = slot(k + 1);
+    if (sb.kind == 2) {
+      TFL_CUDA(cudaMemcpyAsync(x_out, x_in, act_bytes, cudaMemcpyDeviceToDevice, st));
+      if (mixed && tw.fwd16_base != 0) {
+        if (attn_bf16(pl, pk, sb.layer, sb.axis, x_out, d, tw.fwd16, wsp + tw.fwd16_base, st)) return -1;
+      } else if (attn_f32(pl, pk, sb.layer, sb.axis, x_out, d, tw.fwd, wsp, st)) return -1;
+    } else {
+      const FfnPack& f = pl->lay.paths[(size_t)sb.layer * 2 + sb.axis].ffn[sb.kind];
+      FfnTcGeom geom;
+      if (mixed && ffn_tc_geometry(c.emb_dim, f.hidden, c.conv_kernel, c.num_groups, &geom)) {
+        if (tc_ffn(pl, pk, sb.layer, sb.axis, sb.kind, x_in, x_out, B, Tf, F, st)) return -1;
+      } else {
+        TFL_CUDA(cudaMemcpyAsync(x_out, x_in, act_bytes, cudaMemcpyDeviceToDevice, st));
+        if (ffn_f32(pl, pk, sb.layer, sb.axis, sb.kind, x_out, d, tw.fwd, wsp, st)) return -1;
+      }
+    }
   }
-  if (tfl_dec_conv(pl, packed, x, B, Tf, F, est, stream)) return -1;
+  float* x = slot(subs.size());                                  // decoder input
+  if (dec_conv_any(pl, packed, x, B, Tf, F, est, enc_prec, stream)) return -1;
   if (tfl_istft_ola(pl, packed, est, B, Tf, T, audio, stream)) return -1;
   if (est_audio != nullptr)
     TFL_CUDA(cudaMemcpyAsync(est_audio, audio, (size_t)S * B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));

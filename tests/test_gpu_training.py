@@ -28,19 +28,34 @@ def pkg():
     return m
 
 
+MODES = {"fp32": 0, "tf32": 1, "mixed": 2}
+
+
 @pytest.fixture(params=["fp32", "tf32"])
 def gemm_mode(request, pkg):
-    """TFL_OPT_TRAIN_TF32: the training GEMMs as exact fp32 on CUDA cores (parity mode, tight tolerances) or as mma.sync
-    tf32 with fp32 accumulation (the default; 2^-11 per operand, tolerances ~20x wider)."""
+    """TFL_OPT_TRAIN_MODE of the sub-block tests: exact fp32 on CUDA cores (parity mode, tight tolerances) or mma.sync tf32
+    GEMMs with fp32 accumulation (2^-11 per operand, tolerances ~20x wider)."""
     from mss_tf_locoformer_b200 import _lib
     lib = _lib.load()
-    assert lib.tfl_debug_set_option(5, 1 if request.param == "tf32" else 0) == 0
+    assert lib.tfl_debug_set_option(5, MODES[request.param]) == 0
     yield request.param
-    lib.tfl_debug_set_option(5, 1)
+    lib.tfl_debug_set_option(5, 2)
+
+
+@pytest.fixture(params=["fp32", "tf32", "mixed"])
+def train_mode(request, pkg):
+    """TFL_OPT_TRAIN_MODE of the whole-step tests; "mixed" (the default) adds the bf16 tcgen05 forward of the sub-blocks:
+    the gradient is then taken at activations that carry bf16 rounding (~46 dB), as under the reference's autocast."""
+    from mss_tf_locoformer_b200 import _lib
+    lib = _lib.load()
+    assert lib.tfl_debug_set_option(5, MODES[request.param]) == 0
+    yield request.param
+    lib.tfl_debug_set_option(5, 2)
 
 
 # (step: deconv.bias is a sum of terms that largely cancel -- 2.5e-3 against float64 in fp32 mode, everything else < 2e-5)
-TOL = {"fp32": dict(dx=1e-4, grad=1e-3, step=5e-3, loss=2e-4), "tf32": dict(dx=5e-3, grad=2e-2, step=3e-2, loss=3e-3)}
+TOL = {"fp32": dict(dx=1e-4, grad=1e-3, step=5e-3, loss=2e-4), "tf32": dict(dx=5e-3, grad=2e-2, step=3e-2, loss=3e-3),
+       "mixed": dict(step=3e-2, loss=3e-3)}
 
 
 def _rel(got, want):
@@ -156,7 +171,8 @@ def _reference_step(cfg, sd, mix, tgt, weights):
     (dict(SMALL, tf_order="tf", ffn_type="swiglu_conv1d", ffn_hidden_dim=64), 5000, 1, (1.0, 0.1, 0.15)),
     (SMALL, 3000, 1, (1.0, 0.5, 0.0)),
 ])
-def test_train_step_gradients_vs_reference_autograd(pkg, gemm_mode, cfg, n_samples, batch, weights):
+def test_train_step_gradients_vs_reference_autograd(pkg, train_mode, cfg, n_samples, batch, weights):
+    gemm_mode = train_mode
     """tfl_train_forward_backward: total loss, per-source components and EVERY parameter gradient of
     TFLocoformerMSS + MSSLoss against the reference's autograd."""
     from mss_tf_locoformer_b200.training import Trainer
@@ -252,12 +268,12 @@ def test_trainer_steps_follow_reference_optimiser(pkg):
         ref_sd, ref_losses = None, None
     model = model.cuda()
     tr = Trainer(model, lr=1e-3, weight_decay=0.01, si_sdr_weight=weights[0], l1_weight=weights[1], spectral_weight=weights[2])
-    losses = [float(tr.step(mix.cuda(), tgt.cuda())[0]) for _ in range(3)]
+    losses = [float(tr.step(mix.cuda(), tgt.cuda())[0]) for _ in range(3)]      # default mode: mixed
     assert losses[2] < losses[0], losses
     got_sd = model.state_dict()
     if ref_sd is not None:
         for a, b in zip(losses, ref_losses):
-            assert abs(a - b) <= 5e-3 * max(1.0, abs(b)), (losses, ref_losses)
+            assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (losses, ref_losses)
         num = den = 0.0
         for k in tr.engine.keys:
             if k.endswith("rope.freqs"):
@@ -266,7 +282,7 @@ def test_trainer_steps_follow_reference_optimiser(pkg):
             upd_got = got_sd[k].detach().double().cpu() - sd[k].double()
             num += float((upd_got - upd_ref).pow(2).sum())
             den += float(upd_ref.pow(2).sum())
-        assert math.sqrt(num / den) < 0.05, math.sqrt(num / den)
+        assert math.sqrt(num / den) < 0.10, math.sqrt(num / den)   # Adam normalises: the update error ~ the gradient's direction error
     # the forward path sees the updated weights (packed image refreshed after the optimiser kernels)
     with torch.no_grad():
         out = model(mix.cuda())
@@ -321,7 +337,7 @@ def test_data_parallel_two_gpus_matches_one_gpu_batch_of_two(pkg):
         torch.cuda.synchronize()
         params_one = tr.params.cpu().clone()
     finally:
-        lib.tfl_debug_set_option(5, 1)
+        lib.tfl_debug_set_option(5, 2)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -333,3 +349,26 @@ def test_data_parallel_two_gpus_matches_one_gpu_batch_of_two(pkg):
     assert _rel(res[0][0], grads_one) < 1e-4, _rel(res[0][0], grads_one)
     assert float((res[0][1] - params_one).abs().max()) <= 2e-4                           # lr 1e-3: a flipped sign would be 2e-3
     assert abs(float(0.5 * (res[0][2][0] + res[1][2][0])) - float(loss[0])) <= 1e-4 * abs(float(loss[0]))
+
+
+def test_train_step_variant_d_widths_one_layer(pkg, train_mode):
+    """The whole step at production widths (n_fft 2048, emb 128, hidden 384, head_dim 32; one layer, 0.55 s of audio):
+    every tcgen05 forward kernel of the mixed mode and the 128-wide GEMM tiles of the backward pass."""
+    from mss_tf_locoformer_b200.training import Trainer
+    from test_gpu_parity import VARIANT_D
+    cfg = dict(VARIANT_D, flash_attention=False)
+    model = _random_model(pkg, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    mix = _mixture(24000, 1)
+    g = torch.Generator().manual_seed(21)
+    tgt = 0.25 * mix[None] + 0.05 * torch.randn(4, 1, 24000, generator=g)
+    weights = (1.0, 0.1, 0.15)
+    want_loss, want_grads, _ = _reference_step(cfg, sd, mix, tgt, weights)
+    tr = Trainer(model.cuda(), si_sdr_weight=weights[0], l1_weight=weights[1], spectral_weight=weights[2])
+    loss, _ = tr.forward_backward(mix.cuda(), tgt.cuda())
+    tol = TOL[train_mode]
+    assert abs(float(loss[0]) - want_loss) <= tol["loss"] * max(1.0, abs(want_loss)), (float(loss[0]), want_loss)
+    errs = {k: _rel(tr.grad_of(k), want_grads[k]) for k in want_grads}
+    worst_key = max(errs, key=errs.get)
+    print(f"[{train_mode}] Variant-D widths: worst relative gradient error {errs[worst_key]:.2e} ({worst_key})")
+    assert errs[worst_key] < tol["step"], (worst_key, errs[worst_key])
