@@ -196,4 +196,185 @@ __global__ void __launch_bounds__(256) tap_wgrad_mma_kernel(TapWgrad p) {
     }
 }
 
+
+// =========================================================================================================================
+// Attention backward on mma.sync m16n8k8 (tf32 operands, fp32 accumulation): the tensor-core form of attn_bwd_dq_kernel /
+// attn_bwd_dkv_kernel (kernels_bwd.cuh; same buffers, same math).  A warp owns 16 queries (dq) or 16 keys (dk, dv); the other
+// side is staged 64 rows at a time in shared memory as tf32 [row][HD + 4] (every fragment load below hits 32 distinct
+// banks).  Per 8-wide tile of the other side:
+//   S   = Q K^T and dP = dO V^T       A = own rows (registers, loaded once), B = staged rows: b = X[n = g][k = 8 ks + t (+4)]
+//   P   = exp(S - lse),  dS = P (dP - D)          in the accumulator layout: (row g, cols 2t, 2t+1), (row g + 8, same cols)
+//   dQ += dS K   (dV += P^T dO, dK += dS^T Q)     the accumulator IS the A fragment once k slot t is read as column 2t and
+//                                                 slot t + 4 as column 2t + 1 (the order of k inside an MMA is free as long
+//                                                 as B uses the same one: b = X[2t (+1)][n = 8 j + g]) -- no shuffles.
+// =========================================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                              const float* __restrict__ v, const float* __restrict__ o,
+                                                              const float* __restrict__ dO, const float* __restrict__ lse,
+                                                              float* __restrict__ dq, float* __restrict__ Dbuf,
+                                                              int L, int hd, int heads, float scale) {
+  constexpr int TK = 64, PITCH = HD + 4, KS = HD / 8;
+  __shared__ uint32_t ks_[TK][PITCH], vs_[TK][PITCH];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16 + g, r1 = r0 + 8;          // this lane's two query rows
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  const size_t A = (size_t)heads * hd;
+  uint32_t aq[KS][4], ado[KS][4];
+  float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = (e & 1) ? r1 : r0, d = 8 * ks + t + ((e & 2) ? 4 : 0);
+      const bool ok = r < L && d < hd;
+      const float qv = ok ? q[base + (size_t)r * hd + d] * scale : 0.f;
+      const float gv = ok ? dO[((size_t)s * L + r) * A + (size_t)head * hd + d] : 0.f;
+      const float ov = ok ? o[((size_t)s * L + r) * A + (size_t)head * hd + d] : 0.f;
+      aq[ks][e] = to_tf32(qv); ado[ks][e] = to_tf32(gv);
+      if (e & 1) D1 = fmaf(gv, ov, D1); else D0 = fmaf(gv, ov, D0);
+    }
+  }
+  D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+  D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+  const size_t lrow = ((size_t)s * heads + head) * L;
+  const float l0 = r0 < L ? lse[lrow + r0] : 0.f, l1 = r1 < L ? lse[lrow + r1] : 0.f;
+  if (t == 0) {
+    if (r0 < L) Dbuf[lrow + r0] = D0;
+    if (r1 < L) Dbuf[lrow + r1] = D1;
+  }
+  float acc[KS][4];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int j0 = 0; j0 < L; j0 += TK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TK * HD; e += blockDim.x) {
+      const int jj = e / HD, d = e - jj * HD;
+      const bool ok = (j0 + jj < L) && (d < hd);
+      ks_[jj][d] = to_tf32(ok ? k[base + (size_t)(j0 + jj) * hd + d] : 0.f);
+      vs_[jj][d] = to_tf32(ok ? v[base + (size_t)(j0 + jj) * hd + d] : 0.f);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int nt = 0; nt < TK / 8; ++nt) {
+      const int key0 = nt * 8;
+      if (j0 + key0 >= L) break;
+      float S[4] = {0.f, 0.f, 0.f, 0.f}, dP[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bk[2] = {ks_[key0 + g][8 * ks + t], ks_[key0 + g][8 * ks + t + 4]};
+        const uint32_t bv[2] = {vs_[key0 + g][8 * ks + t], vs_[key0 + g][8 * ks + t + 4]};
+        mma_tf32(S, aq[ks], bk);
+        mma_tf32(dP, ado[ks], bv);
+      }
+      const bool v0 = j0 + key0 + 2 * t < L, v1 = j0 + key0 + 2 * t + 1 < L;
+      const float p0 = v0 ? __expf(S[0] - l0) : 0.f, p1 = v1 ? __expf(S[1] - l0) : 0.f;
+      const float p2 = v0 ? __expf(S[2] - l1) : 0.f, p3 = v1 ? __expf(S[3] - l1) : 0.f;
+      // A fragment of dS: (row g, slot t = key 2t), (row g + 8, slot t), (row g, slot t + 4 = key 2t + 1), (row g + 8, slot t + 4)
+      const uint32_t ads[4] = {to_tf32(p0 * (dP[0] - D0)), to_tf32(p2 * (dP[2] - D1)), to_tf32(p1 * (dP[1] - D0)), to_tf32(p3 * (dP[3] - D1))};
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const uint32_t b[2] = {ks_[key0 + 2 * t][8 * j + g], ks_[key0 + 2 * t + 1][8 * j + g]};
+        mma_tf32(acc[j], ads, b);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    const int d = 8 * j + 2 * t;
+    if (d < hd) {
+      if (r0 < L) *reinterpret_cast<float2*>(dq + base + (size_t)r0 * hd + d) = make_float2(acc[j][0] * scale, acc[j][1] * scale);
+      if (r1 < L) *reinterpret_cast<float2*>(dq + base + (size_t)r1 * hd + d) = make_float2(acc[j][2] * scale, acc[j][3] * scale);
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                               const float* __restrict__ v, const float* __restrict__ dO,
+                                                               const float* __restrict__ lse, const float* __restrict__ Dbuf,
+                                                               float* __restrict__ dk, float* __restrict__ dv,
+                                                               int L, int hd, int heads, float scale) {
+  constexpr int TQ = 64, PITCH = HD + 4, KS = HD / 8;
+  __shared__ uint32_t qs_[TQ][PITCH], dos_[TQ][PITCH];
+  __shared__ float ls_[TQ], Ds_[TQ];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16 + g, r1 = r0 + 8;          // this lane's two key rows
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  const size_t A = (size_t)heads * hd;
+  const size_t lrow = ((size_t)s * heads + head) * L;
+  uint32_t ak[KS][4], av[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = (e & 1) ? r1 : r0, d = 8 * ks + t + ((e & 2) ? 4 : 0);
+      const bool ok = r < L && d < hd;
+      ak[ks][e] = to_tf32(ok ? k[base + (size_t)r * hd + d] : 0.f);
+      av[ks][e] = to_tf32(ok ? v[base + (size_t)r * hd + d] : 0.f);
+    }
+  }
+  float dK[KS][4], dV[KS][4];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    dK[j][0] = dK[j][1] = dK[j][2] = dK[j][3] = 0.f;
+    dV[j][0] = dV[j][1] = dV[j][2] = dV[j][3] = 0.f;
+  }
+  for (int i0 = 0; i0 < L; i0 += TQ) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TQ * HD; e += blockDim.x) {
+      const int ii = e / HD, d = e - ii * HD;
+      const bool ok = (i0 + ii < L) && (d < hd);
+      qs_[ii][d] = to_tf32(ok ? q[base + (size_t)(i0 + ii) * hd + d] * scale : 0.f);
+      dos_[ii][d] = to_tf32(ok ? dO[((size_t)s * L + i0 + ii) * A + (size_t)head * hd + d] : 0.f);
+    }
+    for (int e = threadIdx.x; e < TQ; e += blockDim.x) {
+      const bool ok = i0 + e < L;
+      ls_[e] = ok ? lse[lrow + i0 + e] : INFINITY;                       // exp(S - inf) = 0: queries beyond the sequence
+      Ds_[e] = ok ? Dbuf[lrow + i0 + e] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int nt = 0; nt < TQ / 8; ++nt) {
+      const int qq0 = nt * 8;
+      if (i0 + qq0 >= L) break;
+      float ST[4] = {0.f, 0.f, 0.f, 0.f}, dPT[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bq[2] = {qs_[qq0 + g][8 * ks + t], qs_[qq0 + g][8 * ks + t + 4]};
+        const uint32_t bd[2] = {dos_[qq0 + g][8 * ks + t], dos_[qq0 + g][8 * ks + t + 4]};
+        mma_tf32(ST, ak[ks], bq);
+        mma_tf32(dPT, av[ks], bd);
+      }
+      const float la = ls_[qq0 + 2 * t], lb = ls_[qq0 + 2 * t + 1], da = Ds_[qq0 + 2 * t], db = Ds_[qq0 + 2 * t + 1];
+      const float p0 = __expf(ST[0] - la), p1 = __expf(ST[1] - lb), p2 = __expf(ST[2] - la), p3 = __expf(ST[3] - lb);
+      const uint32_t ap[4] = {to_tf32(p0), to_tf32(p2), to_tf32(p1), to_tf32(p3)};
+      const uint32_t ads[4] = {to_tf32(p0 * (dPT[0] - da)), to_tf32(p2 * (dPT[2] - da)), to_tf32(p1 * (dPT[1] - db)), to_tf32(p3 * (dPT[3] - db))};
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const uint32_t bo[2] = {dos_[qq0 + 2 * t][8 * j + g], dos_[qq0 + 2 * t + 1][8 * j + g]};
+        const uint32_t bq[2] = {qs_[qq0 + 2 * t][8 * j + g], qs_[qq0 + 2 * t + 1][8 * j + g]};
+        mma_tf32(dV[j], ap, bo);
+        mma_tf32(dK[j], ads, bq);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    const int d = 8 * j + 2 * t;
+    if (d < hd) {   // qs_ carries the softmax scale already: dK_j = sum_i dS_ij * (scale * Q_i)
+      if (r0 < L) {
+        *reinterpret_cast<float2*>(dk + base + (size_t)r0 * hd + d) = make_float2(dK[j][0], dK[j][1]);
+        *reinterpret_cast<float2*>(dv + base + (size_t)r0 * hd + d) = make_float2(dV[j][0], dV[j][1]);
+      }
+      if (r1 < L) {
+        *reinterpret_cast<float2*>(dk + base + (size_t)r1 * hd + d) = make_float2(dK[j][2], dK[j][3]);
+        *reinterpret_cast<float2*>(dv + base + (size_t)r1 * hd + d) = make_float2(dV[j][2], dV[j][3]);
+      }
+    }
+  }
+}
+
 }  // namespace tfl

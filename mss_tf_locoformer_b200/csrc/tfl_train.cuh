@@ -278,6 +278,19 @@ static int attn_backward(const tfl_plan* pl, const char* packed, int layer, int 
   if (wgrad_launch(gwo, pl->sm_count, st)) return -1;
   const size_t per = (size_t)nseq * heads * L * hd;
   const float scale = 1.0f / sqrtf((float)hd);
+  if (g_gemm_tf32 && hd % 2 == 0 && hd > 8 && hd <= 32) {   // tensor-core form (tf32 mma.sync), 64 rows per block
+    dim3 grid64((L + 63) / 64, heads, nseq);
+    if (hd <= 16) {
+      attn_bwd_dq_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, dO, lse, dqkv_h, Dbuf, L, hd, heads, scale);
+      TFL_LAUNCH_CHECK();
+      attn_bwd_dkv_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, dO, lse, Dbuf, dqkv_h + per, dqkv_h + 2 * per, L, hd, heads, scale);
+    } else {
+      attn_bwd_dq_mma_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, dO, lse, dqkv_h, Dbuf, L, hd, heads, scale);
+      TFL_LAUNCH_CHECK();
+      attn_bwd_dkv_mma_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, dO, lse, Dbuf, dqkv_h + per, dqkv_h + 2 * per, L, hd, heads, scale);
+    }
+    TFL_LAUNCH_CHECK();
+  } else {
   dim3 grid((L + 127) / 128, heads, nseq);
 #define DQ_CASE(HD) attn_bwd_dq_kernel<HD><<<grid, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, dO, lse, dqkv_h, Dbuf, L, hd, heads, scale)
   if (hd <= 8) DQ_CASE(8); else if (hd <= 16) DQ_CASE(16); else if (hd <= 32) DQ_CASE(32); else DQ_CASE(64);
@@ -287,6 +300,7 @@ static int attn_backward(const tfl_plan* pl, const char* packed, int layer, int 
   if (hd <= 8) DKV_CASE(8); else if (hd <= 16) DKV_CASE(16); else if (hd <= 32) DKV_CASE(32); else DKV_CASE(64);
 #undef DKV_CASE
   TFL_LAUNCH_CHECK();
+  }
   {
     const long long total = (long long)3 * nseq * heads * L * (hd / 2);
     long long blocks = (total + 255) / 256;

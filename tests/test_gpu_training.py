@@ -97,7 +97,11 @@ def test_ffn_backward_vs_autograd(pkg, gemm_mode, cfg, shape):
                 assert _rel(grad_of(k), want) < tol["grad"], (k, _rel(grad_of(k), want))
 
 
-@pytest.mark.parametrize("cfg,shape", [(SMALL, (2, 9, 21)), (WIDE, (1, 3, 150)), (dict(SMALL, pos_enc="nope"), (1, 4, 33))])
+HD16 = dict(SMALL, n_layers=1, emb_dim=64, attention_dim=64, ffn_hidden_dim=[64, 64])   # head_dim 16 (the xlarge config's)
+
+
+@pytest.mark.parametrize("cfg,shape", [(SMALL, (2, 9, 21)), (WIDE, (1, 3, 150)), (dict(SMALL, pos_enc="nope"), (1, 4, 33)),
+                                       (HD16, (1, 70, 131)), (WIDE, (2, 67, 9))])
 def test_attention_backward_vs_autograd(pkg, gemm_mode, cfg, shape):
     """tfl_rope_attn_bwd: dx, d gamma, d qkv.weight, d aggregate_heads.weight of x + Wo MHSA(RoPE(qkv(norm(x))))."""
     from mss_tf_locoformer_b200 import training
