@@ -377,4 +377,93 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
   }
 }
 
+// Forward attention with the log-sum-exp kept (training forward in TFL_OPT_TRAIN_MODE 1 and the recompute of the backward
+// pass): the mma form of attn_f32_kernel.  16 queries per warp, 64 keys per stage; S of the whole stage first (8 tiles),
+// one online-softmax update per stage, then P V with the accumulator-as-A-fragment trick above.
+template <int HD>
+__global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                           const float* __restrict__ v, float* __restrict__ o,
+                                                           int L, int hd, int heads, float scale, float* __restrict__ lse) {
+  constexpr int TK = 64, PITCH = HD + 4, KS = HD / 8;
+  __shared__ uint32_t ks_[TK][PITCH], vs_[TK][PITCH];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16 + g, r1 = r0 + 8;
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  const size_t A = (size_t)heads * hd;
+  uint32_t aq[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = (e & 1) ? r1 : r0, d = 8 * ks + t + ((e & 2) ? 4 : 0);
+      aq[ks][e] = to_tf32((r < L && d < hd) ? q[base + (size_t)r * hd + d] * scale : 0.f);
+    }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float acc[KS][4];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int j0 = 0; j0 < L; j0 += TK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TK * HD; e += blockDim.x) {
+      const int jj = e / HD, d = e - jj * HD;
+      const bool ok = (j0 + jj < L) && (d < hd);
+      ks_[jj][d] = to_tf32(ok ? k[base + (size_t)(j0 + jj) * hd + d] : 0.f);
+      vs_[jj][d] = to_tf32(ok ? v[base + (size_t)(j0 + jj) * hd + d] : 0.f);
+    }
+    __syncthreads();
+    float S[TK / 8][4];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < TK / 8; ++nt) {
+      S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bk[2] = {ks_[nt * 8 + g][8 * ks + t], ks_[nt * 8 + g][8 * ks + t + 4]};
+        mma_tf32(S[nt], aq[ks], bk);
+      }
+      const int c0 = j0 + nt * 8 + 2 * t;
+      if (c0 >= L) { S[nt][0] = -INFINITY; S[nt][2] = -INFINITY; }
+      if (c0 + 1 >= L) { S[nt][1] = -INFINITY; S[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);        // finite: every stage holds at least one key < L
+    const float a0 = __expf(m0 - n0), a1 = __expf(m1 - n1);
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) { acc[j][0] *= a0; acc[j][1] *= a0; acc[j][2] *= a1; acc[j][3] *= a1; }
+    m0 = n0; m1 = n1;
+#pragma unroll
+    for (int nt = 0; nt < TK / 8; ++nt) {
+      const float p0 = __expf(S[nt][0] - n0), p1 = __expf(S[nt][1] - n0), p2 = __expf(S[nt][2] - n1), p3 = __expf(S[nt][3] - n1);
+      l0 += p0 + p1; l1 += p2 + p3;
+      const uint32_t ap[4] = {to_tf32(p0), to_tf32(p2), to_tf32(p1), to_tf32(p3)};
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const uint32_t b[2] = {vs_[nt * 8 + 2 * t][8 * j + g], vs_[nt * 8 + 2 * t + 1][8 * j + g]};
+        mma_tf32(acc[j], ap, b);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    const int d = 8 * j + 2 * t;
+    if (d < hd) {
+      if (r0 < L) *reinterpret_cast<float2*>(o + ((size_t)s * L + r0) * A + (size_t)head * hd + d) = make_float2(acc[j][0] * i0, acc[j][1] * i0);
+      if (r1 < L) *reinterpret_cast<float2*>(o + ((size_t)s * L + r1) * A + (size_t)head * hd + d) = make_float2(acc[j][2] * i1, acc[j][3] * i1);
+    }
+  }
+  if (lse != nullptr && t == 0) {
+    const size_t lrow = ((size_t)s * heads + head) * L;
+    if (r0 < L) lse[lrow + r0] = m0 + logf(l0);
+    if (r1 < L) lse[lrow + r1] = m1 + logf(l1);
+  }
+}
+
 }  // namespace tfl

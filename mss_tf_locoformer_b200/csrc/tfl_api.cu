@@ -384,10 +384,16 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
   if (gemm_launch(g1, e1, st)) return -1;
   const size_t per = (size_t)nseq * heads * L * hd;
   const float scale = 1.0f / sqrtf((float)hd);
+  if (g_gemm_tf32 && hd % 2 == 0 && hd > 8 && hd <= 32) {   // training modes >= 1: tf32 mma.sync form (kernels_mma.cuh)
+    dim3 grid64((L + 63) / 64, heads, nseq);
+    if (hd <= 16) attn_fwd_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
+    else attn_fwd_mma_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
+  } else {
   dim3 grid((L + 127) / 128, heads, nseq);
 #define ATT_CASE(HD) attn_f32_kernel<HD><<<grid, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse)
   if (hd <= 8) ATT_CASE(8); else if (hd <= 16) ATT_CASE(16); else if (hd <= 32) ATT_CASE(32); else ATT_CASE(64);
 #undef ATT_CASE
+  }
   TFL_LAUNCH_CHECK();
   if (forward_only_to_o) return 0;
   TapGemm g2{o, make_dense_map((long long)L * A, A), L, L, 0, 1, A, (const float*)(packed + p.wo), nullptr, C,
