@@ -324,7 +324,8 @@ def time_reference_gpu_train(cfg, sd, dev, mix, tgt, steps, loss_w):
             torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=5.0)
             opt.step()
             return loss
-        one()
+        for _ in range(3):                      # cuDNN / cuBLAS algorithm selection and the allocator settle in the first steps
+            one()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -407,7 +408,7 @@ def run_train(args, dev, rank, world):
     ref = None
     if args.reference_gpu:
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-        ref = time_reference_gpu_train(cfg, sd, dev, mix, tgt, max(1, args.steps // 2), loss_w)
+        ref = time_reference_gpu_train(cfg, sd, dev, mix, tgt, max(3, args.steps), loss_w)
     ls = [float(x) for x in torch.cat(losses).cpu()]
     print(json.dumps({
         "metric": "trained audio-sec/sec (forward + loss + backward + gradient all-reduce + clip + AdamW)",

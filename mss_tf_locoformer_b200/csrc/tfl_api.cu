@@ -328,13 +328,15 @@ static int norm_launch(const float* x, float* y, long long rows, int C, int G, c
 
 // Set (per thread, for the duration of a call) by the training entry points when tf32 tensor-core GEMMs are selected
 // (tfl_train.cuh); the inference / parity path never sets it: TFL_PRECISION_FP32 stays exact fp32 on CUDA cores.
-static thread_local bool g_gemm_tf32 = false;
+static thread_local int g_gemm_mode = 0;   // 0 = fp32 CUDA cores, 1 = tf32 mma.sync, 2 = bf16 mma.sync (fp32 accumulation)
+#define g_gemm_tf32 (g_gemm_mode != 0)
 
 template <class Epi>
 static int gemm_launch(const TapGemm& g, const Epi& epi, cudaStream_t st) {
   TFL_CHECK(g.Kc % GBK == 0 && g.N % 4 == 0, "tap-GEMM needs Kc %% 8 == 0 and N %% 4 == 0 (Kc %d N %d)", g.Kc, g.N);
   dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
-  if (g_gemm_tf32 && g.Kc % MMA_BK == 0) tap_gemm_mma_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
+  if (g_gemm_mode == 2 && g.Kc % 32 == 0) tap_gemm_mma_kernel<Epi, true><<<grid, 256, 0, st>>>(g, epi);
+  else if (g_gemm_mode != 0 && g.Kc % MMA_BK == 0) tap_gemm_mma_kernel<Epi, false><<<grid, 256, 0, st>>>(g, epi);
   else tap_gemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
   TFL_LAUNCH_CHECK();
   return 0;

@@ -128,9 +128,10 @@ static int wgrad_launch(TapWgrad g, int sm_count, cudaStream_t st) {
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
-  g.rows_per_split = ((g.R + splits - 1) / splits + MMA_BK - 1) / MMA_BK * MMA_BK;
+  g.rows_per_split = ((g.R + splits - 1) / splits + 31) / 32 * 32;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
-  if (g_gemm_tf32) tap_wgrad_mma_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
+  if (g_gemm_mode == 2) tap_wgrad_mma_kernel<true><<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
+  else if (g_gemm_mode == 1) tap_wgrad_mma_kernel<false><<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   else tap_wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   TFL_LAUNCH_CHECK();
   return 0;
@@ -334,10 +335,10 @@ static std::vector<SubBlock> sub_blocks(const tfl_plan* pl) {
   return v;
 }
 
-struct Tf32Scope {   // GEMM arithmetic of one training call: TFL_OPT_TRAIN_MODE >= 1 selects tf32 MMAs; restored on exit
-  bool prev;
-  Tf32Scope() : prev(g_gemm_tf32) { g_gemm_tf32 = tfl_option(TFL_OPT_TRAIN_MODE) != 0; }
-  ~Tf32Scope() { g_gemm_tf32 = prev; }
+struct Tf32Scope {   // GEMM arithmetic of one training call = TFL_OPT_TRAIN_MODE (0 fp32, 1 tf32, 2 bf16 MMAs); restored on exit
+  int prev;
+  Tf32Scope() : prev(g_gemm_mode) { const int m = tfl_option(TFL_OPT_TRAIN_MODE); g_gemm_mode = m < 0 ? 0 : (m > 2 ? 2 : m); }
+  ~Tf32Scope() { g_gemm_mode = prev; }
 };
 
 static int check_train(const tfl_plan* pl, const void* packed, const float* const* w, int n_weights) {
