@@ -376,3 +376,26 @@ def test_train_step_variant_d_widths_one_layer(pkg, train_mode):
     worst_key = max(errs, key=errs.get)
     print(f"[{train_mode}] Variant-D widths: worst relative gradient error {errs[worst_key]:.2e} ({worst_key})")
     assert errs[worst_key] < tol["step"], (worst_key, errs[worst_key])
+
+
+def test_train_step_xlarge_widths_one_layer(pkg, train_mode):
+    """musdb18_rtx5090_xlarge.yaml widths (emb 256, 16 heads x 16, 8 groups, hidden 1024) at a small n_fft, one layer: two
+    128-wide tiles along every GEMM dimension, head_dim 16, and -- in mixed mode -- the tcgen05 FFN forward at emb 256 with
+    the attention (outside the tcgen05 kernel's shapes) on the tf32 path."""
+    from mss_tf_locoformer_b200.training import Trainer
+    cfg = dict(SMALL, n_layers=1, emb_dim=256, attention_dim=256, n_heads=16, num_groups=8, ffn_hidden_dim=[1024, 1024])
+    model = _random_model(pkg, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    mix = _mixture(3000, 1)
+    g = torch.Generator().manual_seed(31)
+    tgt = 0.25 * mix[None] + 0.05 * torch.randn(4, 1, 3000, generator=g)
+    weights = (1.0, 0.1, 0.15)
+    want_loss, want_grads, _ = _reference_step(cfg, sd, mix, tgt, weights)
+    tr = Trainer(model.cuda(), si_sdr_weight=weights[0], l1_weight=weights[1], spectral_weight=weights[2])
+    loss, _ = tr.forward_backward(mix.cuda(), tgt.cuda())
+    tol = TOL[train_mode]
+    assert abs(float(loss[0]) - want_loss) <= tol["loss"] * max(1.0, abs(want_loss)), (float(loss[0]), want_loss)
+    errs = {k: _rel(tr.grad_of(k), want_grads[k]) for k in want_grads}
+    worst_key = max(errs, key=errs.get)
+    print(f"[{train_mode}] xlarge widths: worst relative gradient error {errs[worst_key]:.2e} ({worst_key})")
+    assert errs[worst_key] < tol["step"], (worst_key, errs[worst_key])
