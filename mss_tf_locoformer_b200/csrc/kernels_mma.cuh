@@ -191,19 +191,38 @@ __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
   const long long r_hi = r_lo + p.rows_per_split < p.R ? r_lo + p.rows_per_split : p.R;
   if (r_lo >= r_hi) return;
   const int l_row = tid >> 5, l_col = (tid & 31) << 2;
-  // tf32: rows r0 + l_row and r0 + l_row + 8;  bf16: rows r0 + 4 l_row .. + 3 (two row PAIRS: words 2 l_row, 2 l_row + 1)
-  auto load = [&](long long r0, float4 (&a)[NV], float4 (&b)[NV]) {
+  // tf32: rows r0 + l_row and r0 + l_row + 8;  bf16: rows r0 + 4 l_row .. + 3 (two row PAIRS: words 2 l_row, 2 l_row + 1).
+  // The (sequence, position) of the thread's FIRST row is carried from round to round (the rows advance by RK): the 64-bit
+  // divisions of a per-load r / Sout and the SeqMap bases were most of this kernel's instructions (ncu r02: issue 52 %
+  // active against a tensor pipe at 17 %).
+  constexpr int RSTEP = BF16 ? 1 : 8;                     // distance between the thread's rows
+  long long row_first = r_lo + (BF16 ? 4 * l_row : l_row);
+  int s_first = (int)(row_first / p.Sout), j_first = (int)(row_first - (long long)s_first * p.Sout);
+  long long abase = p.amap.base(s_first), bbase = p.bmap.base(s_first);
+  auto advance = [&]() {
+    row_first += RK; j_first += RK;
+    if (j_first >= p.Sout) {
+      do { j_first -= p.Sout; ++s_first; } while (j_first >= p.Sout);
+      abase = p.amap.base(s_first); bbase = p.bmap.base(s_first);
+    }
+  };
+  auto load = [&](float4 (&a)[NV], float4 (&b)[NV]) {     // the rows at the carried position
 #pragma unroll
     for (int h = 0; h < NV; ++h) {
       a[h] = make_float4(0.f, 0.f, 0.f, 0.f); b[h] = a[h];
-      const long long r = BF16 ? r0 + 4 * l_row + h : r0 + l_row + 8 * h;
-      if (r >= r_hi) continue;
-      const int s = (int)(r / p.Sout), j = (int)(r - (long long)s * p.Sout);
+      if (row_first + h * RSTEP >= r_hi) continue;
+      int j = j_first + h * RSTEP;
+      long long ab = abase, bb = bbase;
+      if (j >= p.Sout) {                                    // this row belongs to a later sequence (rare)
+        int sq = s_first;
+        do { j -= p.Sout; ++sq; } while (j >= p.Sout);
+        ab = p.amap.base(sq); bb = p.bmap.base(sq);
+      }
       const int pos = j + tap - p.padL;
       if (pos >= 0 && pos < p.Sin && i0 + l_col < p.Kc)
-        a[h] = __ldg(reinterpret_cast<const float4*>(p.A + p.amap.base(s) + (long long)pos * p.amap.pos_stride + i0 + l_col));
+        a[h] = __ldg(reinterpret_cast<const float4*>(p.A + ab + (long long)pos * p.amap.pos_stride + i0 + l_col));
       if (n0 + l_col < p.N)
-        b[h] = __ldg(reinterpret_cast<const float4*>(p.B + p.bmap.base(s) + (long long)j * p.bmap.pos_stride + n0 + l_col));
+        b[h] = __ldg(reinterpret_cast<const float4*>(p.B + bb + (long long)j * p.bmap.pos_stride + n0 + l_col));
     }
   };
   auto stash = [&](int buf, const float4 (&a)[NV], const float4 (&b)[NV]) {
@@ -233,13 +252,13 @@ __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
   float4 a[NV], b[NV];
-  load(r_lo, a, b);
+  load(a, b);
   stash(0, a, b);
   __syncthreads();
   int cur = 0;
   for (long long r0 = r_lo; r0 < r_hi; r0 += RK) {
     const bool more = r0 + RK < r_hi;
-    if (more) load(r0 + RK, a, b);
+    if (more) { advance(); load(a, b); }
     mma_warp_step<BF16>(&As[cur][0][0], &Bs[cur][0][0], acc, wm, wn, g, t);
     mma_warp_step<BF16>(&As[cur][8][0], &Bs[cur][8][0], acc, wm, wn, g, t);
     if (more) stash(cur ^ 1, a, b);
