@@ -160,6 +160,9 @@ int tfl_rope_attn_bwd(const tfl_plan* plan, const void* packed, const float* con
  * (device, 2 floats; no host sync).  scratch: >= 592 doubles. */
 int tfl_grad_clip_norm(const float* grads, int64_t n, float max_norm, float* norm_out, double* scratch,
                        size_t scratch_bytes, tfl_stream_t stream);
+/* acc = (overwrite ? 0 : acc) + scale * grads -- gradient accumulation over micro-batches (train.py:117-146, the
+ * `loss / gradient_accumulation_steps` of the reference folded into `scale`). */
+int tfl_grad_accumulate(float* acc, const float* grads, int64_t n, float scale, int overwrite, tfl_stream_t stream);
 /* torch.optim.AdamW step `step` (1-based) over flat buffers (train.py:351-357); `clip` = norm_out above or NULL. */
 int tfl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* clip,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, tfl_stream_t stream);

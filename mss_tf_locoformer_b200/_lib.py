@@ -56,6 +56,7 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_conv_swiglu_ffn_bwd": (_I, [_P, _P, C.POINTER(_P), _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     "tfl_rope_attn_bwd": (_I, [_P, _P, C.POINTER(_P), _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     "tfl_grad_clip_norm": (_I, [_P, _L, _F, _P, _P, _Z, _P]),
+    "tfl_grad_accumulate": (_I, [_P, _P, _L, _F, _I, _P]),
     "tfl_adamw_step": (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),
     "tfl_debug_set_option": (_I, [_I, _I]),
     "tfl_debug_set_trace": (_I, [_P]),

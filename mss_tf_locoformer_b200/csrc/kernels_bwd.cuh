@@ -171,13 +171,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ B
   const int lanes = n4 < 256 ? n4 : 256;             // threads along the columns
   const int rows_par = 256 / lanes;                  // rows handled in parallel by one block
   const int col = (threadIdx.x % lanes), rsub = threadIdx.x / lanes;
-  if (rsub < rows_par) {
+  // every block owns a contiguous run of rows; (sequence, position) is carried along it instead of divided out per row
+  const long long chunk = (R + gridDim.x - 1) / gridDim.x;
+  const long long r_lo = (long long)blockIdx.x * chunk, r_hi = r_lo + chunk < R ? r_lo + chunk : R;
+  if (rsub < rows_par && r_lo + rsub < r_hi) {
     for (int c4 = col; c4 < n4; c4 += lanes) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (long long r = (long long)blockIdx.x * rows_par + rsub; r < R; r += (long long)gridDim.x * rows_par) {
-        const int s = (int)(r / Sout), j = (int)(r - (long long)s * Sout);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(B + bmap.base(s) + (long long)j * bmap.pos_stride + 4 * c4));
+      long long r = r_lo + rsub;
+      int s = (int)(r / Sout), j = (int)(r - (long long)s * Sout);
+      long long base = bmap.base(s);
+      for (; r < r_hi; r += rows_par) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(B + base + (long long)j * bmap.pos_stride + 4 * c4));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        j += rows_par;
+        if (j >= Sout) {
+          do { j -= Sout; ++s; } while (j >= Sout);
+          base = bmap.base(s);
+        }
       }
       atomicAdd(&cs_sm[4 * c4], acc.x); atomicAdd(&cs_sm[4 * c4 + 1], acc.y);
       atomicAdd(&cs_sm[4 * c4 + 2], acc.z); atomicAdd(&cs_sm[4 * c4 + 3], acc.w);
@@ -766,6 +776,12 @@ __global__ void sqnorm_finish_kernel(const double* __restrict__ partial, int n_p
   norm_out[0] = (float)nrm;
   const double coef = (double)max_norm / (nrm + 1e-6);
   norm_out[1] = (float)(coef < 1.0 ? coef : 1.0);
+}
+// acc += scale * g (gradient accumulation over micro-batches, train.py:117-146: loss / gradient_accumulation_steps)
+__global__ void __launch_bounds__(256) grad_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ g, long long n, float scale,
+                                                              int overwrite) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] = overwrite ? scale * g[i] : fmaf(scale, g[i], acc[i]);
 }
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, const float* __restrict__ clip,

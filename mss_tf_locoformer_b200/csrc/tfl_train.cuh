@@ -600,6 +600,16 @@ int tfl_grad_clip_norm(const float* grads, int64_t n, float max_norm, float* nor
   return 0;
 }
 
+// acc = (overwrite ? 0 : acc) + scale * grads: micro-batch gradient accumulation (train.py:117-146).
+int tfl_grad_accumulate(float* acc, const float* grads, int64_t n, float scale, int overwrite, tfl_stream_t stream) {
+  TFL_CHECK(acc && grads && n >= 1, "null / empty argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  grad_accumulate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(acc, grads, (long long)n, scale, overwrite);
+  TFL_LAUNCH_CHECK();
+  return 0;
+}
+
 // torch.optim.AdamW step t (1-based) over flat buffers; `clip` = norm_out of tfl_grad_clip_norm (device) or NULL.
 int tfl_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* clip, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, tfl_stream_t stream) {

@@ -42,7 +42,8 @@ class Trainer:
 
     def __init__(self, model, lr: float = 3e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 5.0, si_sdr_weight: float = 1.0, l1_weight: float = 0.1,
-                 spectral_weight: float = 0.1, loss_eps: float = 1e-8, spec_n_fft: int = 2048, spec_hop: int = 1024):
+                 spectral_weight: float = 0.1, loss_eps: float = 1e-8, spec_n_fft: int = 2048, spec_hop: int = 1024,
+                 gradient_accumulation_steps: int = 1):
         if getattr(model, "_dropout_p", 0.0) > 0.0:
             raise NotImplementedError("training kernels do not apply dropout: construct the model with dropout=0.0")
         self.model = model
@@ -78,6 +79,9 @@ class Trainer:
         self._scratch = torch.zeros(592, dtype=torch.float64, device=dev)
         self._ws: Optional[torch.Tensor] = None
         self._ws_key = None
+        self.gradient_accumulation_steps = int(gradient_accumulation_steps)
+        self._accum: Optional[torch.Tensor] = None
+        self._micro = 0
         model.repack()
 
     # ---- pieces of a step -----------------------------------------------------------------------------------------
@@ -126,11 +130,48 @@ class Trainer:
         self.engine.invalidate()             # the kernels wrote the parameters behind torch's version counters
 
     def step(self, mixture: torch.Tensor, targets) -> torch.Tensor:
-        """One training step (train.py:115-146).  Data parallel: every rank calls it on its own batch."""
+        """One training step (train.py:115-146).  Data parallel: every rank calls it on its own batch.
+
+        With ``gradient_accumulation_steps = N > 1`` (train.py:117-146) the gradients of N consecutive calls are averaged
+        (``loss / N``) and the all-reduce + clip + AdamW run on every N-th call only."""
         loss, _ = self.forward_backward(mixture, targets)
+        n = self.gradient_accumulation_steps
+        if n > 1:
+            if self._accum is None:
+                self._accum = torch.zeros_like(self.grads)
+            with torch.cuda.device(self.params.device):
+                check(self.lib.tfl_grad_accumulate(self._accum.data_ptr(), self.grads.data_ptr(), self.total, 1.0 / n,
+                                                   1 if self._micro == 0 else 0, _stream()))
+            self._micro += 1
+            if self._micro < n:
+                return loss
+            self._micro = 0
+            self.grads, self._accum = self._accum, self.grads      # the optimiser reads self.grads
         allreduce_mean_(self.grads)
         self.optimizer_step()
         return loss
+
+    # ---- checkpoint / resume (train.py: `save_optimizer: true`) ----------------------------------------------------
+    def state_dict(self) -> dict:
+        """Optimiser state per state_dict key, in the reference's tensor shapes (like torch.optim's per-parameter state)."""
+        def views(flat):
+            return {k: flat[o:o + n].view(t.shape).detach().clone()
+                    for k, t, o, n in zip(self.engine.keys, self.tensors, self.offsets, self.sizes) if o >= 0}
+        return {"step": self.step_count, "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
+                "exp_avg": views(self.exp_avg), "exp_avg_sq": views(self.exp_avg_sq)}
+
+    def load_state_dict(self, state: dict):
+        self.step_count = int(state["step"])
+        self.lr, self.betas = float(state["lr"]), tuple(state["betas"])
+        self.eps, self.weight_decay = float(state["eps"]), float(state["weight_decay"])
+        for name, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+            for k, t, o, n in zip(self.engine.keys, self.tensors, self.offsets, self.sizes):
+                if o >= 0:
+                    flat[o:o + n].view(t.shape).copy_(state[name][k])
+
+    def set_lr(self, lr: float):
+        """Learning-rate schedulers (ReduceLROnPlateau, warm-up: train.py:360-371) drive the step size through this."""
+        self.lr = float(lr)
 
     def grad_of(self, key: str) -> torch.Tensor:
         """Gradient of the state_dict tensor ``key`` (a view of the flat buffer, in the reference's layout)."""

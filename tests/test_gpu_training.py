@@ -399,3 +399,42 @@ def test_train_step_xlarge_widths_one_layer(pkg, train_mode):
     worst_key = max(errs, key=errs.get)
     print(f"[{train_mode}] xlarge widths: worst relative gradient error {errs[worst_key]:.2e} ({worst_key})")
     assert errs[worst_key] < tol["step"], (worst_key, errs[worst_key])
+
+
+def test_gradient_accumulation_and_resume(pkg):
+    """train.py:117-146 with gradient_accumulation_steps = 2: two micro-batches of one sample == one step on the batch of
+    two (every loss term is a batch mean); and a Trainer restored from state_dict() continues bit-identically."""
+    from mss_tf_locoformer_b200 import _lib
+    from mss_tf_locoformer_b200.training import Trainer
+    cfg = dict(SMALL, n_layers=1)
+    model_a = _random_model(pkg, cfg).cuda()
+    sd = {k: v.detach().clone() for k, v in model_a.state_dict().items()}
+    mix = _mixture(4000, 2).cuda()
+    g = torch.Generator().manual_seed(4)
+    tgt = (0.25 * mix.cpu()[None] + 0.05 * torch.randn(4, 2, 4000, generator=g)).cuda()
+    lib = _lib.load()
+    lib.tfl_debug_set_option(5, 0)                       # exact fp32: the two orders of summation agree to rounding
+    try:
+        tr_a = Trainer(model_a, lr=1e-3)
+        tr_a.step(mix, tgt)
+        model_b = pkg.TFLocoformerMSS(**cfg)
+        model_b.load_state_dict(sd)
+        tr_b = Trainer(model_b.cuda(), lr=1e-3, gradient_accumulation_steps=2)
+        tr_b.step(mix[0:1], tgt[:, 0:1])
+        assert tr_b.step_count == 0                      # first micro-batch: no optimiser step yet
+        tr_b.step(mix[1:2], tgt[:, 1:2])
+        assert tr_b.step_count == 1
+        assert float((tr_a.params - tr_b.params).abs().max()) <= 2e-4     # lr 1e-3: a flipped update would be 2e-3
+        # resume: a fresh Trainer on the saved model + optimiser state takes the same second step
+        opt_state = tr_a.state_dict()
+        model_c = pkg.TFLocoformerMSS(**cfg)
+        model_c.load_state_dict({k: v.detach().clone() for k, v in model_a.state_dict().items()})
+        tr_c = Trainer(model_c.cuda(), lr=5e-4)
+        tr_c.load_state_dict(opt_state)
+        assert tr_c.lr == tr_a.lr and tr_c.step_count == 1
+        tr_a.step(mix, tgt)
+        tr_c.step(mix, tgt)
+        assert float((tr_a.params - tr_c.params).abs().max()) <= 2e-5     # same inputs; atomics order only
+        assert set(opt_state["exp_avg"]) == {k for k in sd if not k.endswith("rope.freqs")}
+    finally:
+        lib.tfl_debug_set_option(5, 2)
