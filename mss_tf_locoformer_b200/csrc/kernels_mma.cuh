@@ -14,13 +14,13 @@ constexpr int MMA_PITCH = GBM + 8;
 constexpr int MMA_BK = 16;   // k depth per barrier round (two m16n8k8 steps): the 8-deep version ran latency-bound (r02: 89 TFLOP/s)
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -283,6 +283,238 @@ __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
     }
 }
 
+
+// =========================================================================================================================
+// bf16 forms of the two GEMMs with ldmatrix fragment loads (TFL_OPT_TRAIN_MODE 2).  The k-major word tiles above cost 24
+// scalar shared loads per 16 MMAs; here the tiles are bf16 in the layouts ldmatrix wants -- A [m][k] (80-byte pitch),
+// B [k][n] (272-byte pitch, read transposed), the weight gradient's A [k = row][m] (transposed too) -- and a 16-deep step of
+// a warp's 64 x 32 tile is 4 + 2 ldmatrix.x4 for 16 MMAs.  Conversion fp32 -> bf16 happens once, on the way into shared
+// memory.  (Measured: 261 -> 254 ms per Variant-D step -- the kernels stay bound by the latency of the next round's global
+// loads at two blocks per SM, ncu r02; a producer / consumer split like the tcgen05 kernels' is what would lift that.)
+// =========================================================================================================================
+constexpr int BF_AP = 40;    // A tile pitch in bf16 (32 k + 8): rows 80 bytes apart -> 8 consecutive rows hit 8 distinct 16-byte banks
+constexpr int BF_BP = 136;   // [k][n] tile pitch in bf16 (128 + 8): rows 272 bytes apart
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ uint2 pack4_bf16(const float4& v) { return make_uint2(pack2_bf16(v.x, v.y), pack2_bf16(v.z, v.w)); }
+
+// B fragments of the warp's four 8-wide n tiles for one 16-deep step, from a [k][n] bf16 tile (rows k0 .. k0 + 15)
+__device__ __forceinline__ void load_b_frags(uint32_t (&b)[4][2], const __nv_bfloat16* Bs, int k0, int n_base, int lane) {
+#pragma unroll
+  for (int jp = 0; jp < 2; ++jp) {
+    uint32_t r[4];
+    ldmatrix_x4_trans(r, Bs + (size_t)(k0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * BF_BP + n_base + jp * 16 + 8 * (lane >> 4));
+    b[2 * jp][0] = r[0]; b[2 * jp][1] = r[1]; b[2 * jp + 1][0] = r[2]; b[2 * jp + 1][1] = r[3];
+  }
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(256, 2) tap_gemm_bf16_kernel(TapGemm p, Epi epi) {
+  __shared__ __align__(16) __nv_bfloat16 As[2][GBM][BF_AP];
+  __shared__ __align__(16) __nv_bfloat16 Bs[2][32][BF_BP];
+  __shared__ long long row_base[GBM];
+  __shared__ int row_j[GBM], row_s[GBM];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * GBM;
+  const int n0 = blockIdx.y * GBN;
+  if (tid < GBM) {
+    const long long r = m0 + tid;
+    if (r < p.M) {
+      const int s = (int)(r / p.Sout), j = (int)(r - (long long)s * p.Sout);
+      row_s[tid] = s; row_j[tid] = j; row_base[tid] = p.amap.base(s);
+    } else { row_s[tid] = -1; row_j[tid] = 0; row_base[tid] = 0; }
+  }
+  __syncthreads();
+  // per round (k = 32) and thread: A row a_row, k = 16 a_half .. + 15;  B k rows 4 b_row4 .. + 3, columns b_col .. + 3
+  const int a_row = tid >> 1, a_half = tid & 1;
+  const int b_row4 = tid >> 5, b_col = (tid & 31) << 2;
+  const int kt_per_tap = p.Kc / 32, n_kt = p.taps * kt_per_tap;
+  const int my_s = row_s[a_row], my_j = row_j[a_row];
+  const long long my_base = row_base[a_row];
+  auto load_a = [&](int kt, float4 (&a)[4]) {
+    const int tap = kt / kt_per_tap, c0 = (kt - tap * kt_per_tap) * 32;
+    const int pos = my_j + tap - p.padL;
+    if (my_s < 0 || pos < 0 || pos >= p.Sin) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) a[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    const float* src = p.A + my_base + (long long)pos * p.amap.pos_stride + c0 + 16 * a_half;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) a[h] = __ldg(reinterpret_cast<const float4*>(src + 4 * h));
+  };
+  auto load_b = [&](int kt, float4 (&b)[4]) {
+    const int n = n0 + b_col;
+    if (n >= p.N) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) b[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    const float* src = p.W + ((size_t)kt * 32 + 4 * b_row4) * p.N + n;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) b[h] = __ldg(reinterpret_cast<const float4*>(src + (size_t)h * p.N));
+  };
+  auto stash = [&](int buf, const float4 (&a)[4], const float4 (&b)[4]) {
+    const uint2 p0 = pack4_bf16(a[0]), p1 = pack4_bf16(a[1]), p2 = pack4_bf16(a[2]), p3 = pack4_bf16(a[3]);
+    *reinterpret_cast<uint4*>(&As[buf][a_row][16 * a_half]) = make_uint4(p0.x, p0.y, p1.x, p1.y);
+    *reinterpret_cast<uint4*>(&As[buf][a_row][16 * a_half + 8]) = make_uint4(p2.x, p2.y, p3.x, p3.y);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) *reinterpret_cast<uint2*>(&Bs[buf][4 * b_row4 + h][b_col]) = pack4_bf16(b[h]);
+  };
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+  float4 na[4], nb[4];
+  load_a(0, na); load_b(0, nb);
+  stash(0, na, nb);
+  __syncthreads();
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int cur = kt & 1;
+    const bool more = kt + 1 < n_kt;
+    if (more) { load_a(kt + 1, na); load_b(kt + 1, nb); }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4][4], b[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        ldmatrix_x4(a[i], &As[cur][wm * 64 + i * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][ks * 16 + 8 * (lane >> 4)]);
+      load_b_frags(b, &Bs[cur][0][0], ks * 16, wn * 32, lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_bf16(acc[i][j], a[i], b[j]);
+    }
+    if (more) stash(cur ^ 1, na, nb);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + wn * 32 + j * 8 + 2 * t;
+    if (n >= p.N) continue;
+    const float b0 = p.bias != nullptr ? __ldg(&p.bias[n]) : 0.f, b1 = p.bias != nullptr ? __ldg(&p.bias[n + 1]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rl = wm * 64 + i * 16 + g + 8 * h;
+        const int s = row_s[rl];
+        if (s < 0) continue;
+        epi.pair(s, row_j[rl], m0 + rl, n, p.N, acc[i][j][2 * h] + b0, acc[i][j][2 * h + 1] + b1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) tap_wgrad_bf16_kernel(TapWgrad p) {
+  __shared__ __align__(16) __nv_bfloat16 As[2][32][BF_BP];   // [k = row][m = i]
+  __shared__ __align__(16) __nv_bfloat16 Bs[2][32][BF_BP];   // [k = row][n]
+  const int tid = threadIdx.x;
+  const int tiles_i = (p.Kc + GBM - 1) / GBM, tiles_n = (p.N + GBN - 1) / GBN;
+  int bx = blockIdx.x;
+  const int tn = bx % tiles_n; bx /= tiles_n;
+  const int ti = bx % tiles_i; bx /= tiles_i;
+  const int tap = bx;
+  const int i0 = ti * GBM, n0 = tn * GBN;
+  const long long r_lo = (long long)blockIdx.y * p.rows_per_split;
+  const long long r_hi = r_lo + p.rows_per_split < p.R ? r_lo + p.rows_per_split : p.R;
+  if (r_lo >= r_hi) return;
+  const int l_row4 = tid >> 5, l_col = (tid & 31) << 2;    // rows 4 l_row4 .. + 3 of the round, columns l_col .. + 3
+  // (sequence, position) of the thread's first row, carried from round to round (rows advance by 32)
+  long long row_first = r_lo + 4 * l_row4;
+  int s_first = (int)(row_first / p.Sout), j_first = (int)(row_first - (long long)s_first * p.Sout);
+  long long abase = p.amap.base(s_first), bbase = p.bmap.base(s_first);
+  auto advance = [&]() {
+    row_first += 32; j_first += 32;
+    if (j_first >= p.Sout) {
+      do { j_first -= p.Sout; ++s_first; } while (j_first >= p.Sout);
+      abase = p.amap.base(s_first); bbase = p.bmap.base(s_first);
+    }
+  };
+  auto load = [&](float4 (&a)[4], float4 (&b)[4]) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      a[h] = make_float4(0.f, 0.f, 0.f, 0.f); b[h] = a[h];
+      if (row_first + h >= r_hi) continue;
+      int j = j_first + h;
+      long long ab = abase, bb = bbase;
+      if (j >= p.Sout) {                                    // this row belongs to a later sequence (rare)
+        int sq = s_first;
+        do { j -= p.Sout; ++sq; } while (j >= p.Sout);
+        ab = p.amap.base(sq); bb = p.bmap.base(sq);
+      }
+      const int pos = j + tap - p.padL;
+      if (pos >= 0 && pos < p.Sin && i0 + l_col < p.Kc)
+        a[h] = __ldg(reinterpret_cast<const float4*>(p.A + ab + (long long)pos * p.amap.pos_stride + i0 + l_col));
+      if (n0 + l_col < p.N)
+        b[h] = __ldg(reinterpret_cast<const float4*>(p.B + bb + (long long)j * p.bmap.pos_stride + n0 + l_col));
+    }
+  };
+  auto stash = [&](int buf, const float4 (&a)[4], const float4 (&b)[4]) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      *reinterpret_cast<uint2*>(&As[buf][4 * l_row4 + h][l_col]) = pack4_bf16(a[h]);
+      *reinterpret_cast<uint2*>(&Bs[buf][4 * l_row4 + h][l_col]) = pack4_bf16(b[h]);
+    }
+  };
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+  float4 a4[4], b4[4];
+  load(a4, b4);
+  stash(0, a4, b4);
+  __syncthreads();
+  int cur = 0;
+  for (long long r0 = r_lo; r0 < r_hi; r0 += 32) {
+    const bool more = r0 + 32 < r_hi;
+    if (more) { advance(); load(a4, b4); }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4][4], b[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)   // A^T: matrices (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7), (k 8-15, m 8-15) = a0 .. a3
+        ldmatrix_x4_trans(a[i], &As[cur][ks * 16 + (lane & 7) + 8 * (lane >> 4)][wm * 64 + i * 16 + 8 * ((lane >> 3) & 1)]);
+      load_b_frags(b, &Bs[cur][0][0], ks * 16, wn * 32, lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_bf16(acc[i][j], a[i], b[j]);
+    }
+    if (more) stash(cur ^ 1, a4, b4);
+    __syncthreads();
+    cur ^= 1;
+  }
+  float* o = p.out + (size_t)tap * p.Kc * p.N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ii = i0 + wm * 64 + i * 16 + g + 8 * h;
+      if (ii >= p.Kc) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nn = n0 + wn * 32 + j * 8 + 2 * t;
+        if (nn < p.N) {
+          atomicAdd(&o[(size_t)ii * p.N + nn], acc[i][j][2 * h]);
+          atomicAdd(&o[(size_t)ii * p.N + nn + 1], acc[i][j][2 * h + 1]);
+        }
+      }
+    }
+}
 
 // =========================================================================================================================
 // Attention backward on mma.sync m16n8k8 (tf32 operands, fp32 accumulation): the tensor-core form of attn_bwd_dq_kernel /

@@ -130,7 +130,7 @@ static int wgrad_launch(TapWgrad g, int sm_count, cudaStream_t st) {
   if (splits > 65535) splits = 65535;
   g.rows_per_split = ((g.R + splits - 1) / splits + 31) / 32 * 32;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
-  if (g_gemm_mode == 2) tap_wgrad_mma_kernel<true><<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
+  if (g_gemm_mode == 2) tap_wgrad_bf16_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   else if (g_gemm_mode == 1) tap_wgrad_mma_kernel<false><<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   else tap_wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   TFL_LAUNCH_CHECK();
