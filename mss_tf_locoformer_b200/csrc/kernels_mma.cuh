@@ -3,7 +3,8 @@
 // the reference trains in at best (configs/musdb18_rtx5090_xlarge.yaml:136 `tf32: true`, under bf16 autocast).  Same
 // parameters, same 128 x 128 x 8 block tiles and the same epilogue functors (through their two-column `pair` form: an
 // accumulator fragment holds adjacent column pairs).  The fp32 inference / parity mode never runs these kernels.
-//   block = 8 warps as 2 (m) x 4 (n); warp tile 64 x 32 = 4 x 4 fragments, 16 MMAs per 8-deep k step and 24 shared loads.
+//   block = 8 warps as 2 (m) x 4 (n); warp tile 64 x 32 = 4 x 4 fragments, 16 MMAs per 8-deep k step and 24 shared loads (tf32)
+//   or 6 ldmatrix.x4 per 16-deep step (bf16 forms further down).
 //   shared tiles are k-major with a pitch of 136 floats: fragment loads (k = t or t + 4, m / n = g) hit 32 distinct banks.
 #pragma once
 #include "kernels_bwd.cuh"
@@ -29,10 +30,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {   // low ha
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// One step of the warp's 64 x 32 tile over an [8 words][MMA_PITCH] tile pair.  tf32: a word is one tf32 value, the step is
-// 8 deep (m16n8k8).  BF16: a word is the bf16 pair (k = 2w, 2w + 1), the step is 16 deep (m16n8k16) -- the fragment
-// addressing is the same with "k" read as the pair index, half the MMAs and half the shared loads per unit of k.
-template <bool BF16>
+// one 8-deep step (m16n8k8) of the warp's 64 x 32 tile over an [8][MMA_PITCH] tile pair holding tf32 bit patterns
 __device__ __forceinline__ void mma_warp_step(const uint32_t* As, const uint32_t* Bs, float (&acc)[4][4][4], int wm, int wn, int g, int t) {
   uint32_t a[4][4], b[4][2];
 #pragma unroll
@@ -49,14 +47,11 @@ __device__ __forceinline__ void mma_warp_step(const uint32_t* As, const uint32_t
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (BF16) mma_bf16(acc[i][j], a[i], b[j]); else mma_tf32(acc[i][j], a[i], b[j]);
-    }
+    for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], a[i], b[j]);
 }
 
-template <class Epi, bool BF16>
+template <class Epi>
 __global__ void __launch_bounds__(256, 2) tap_gemm_mma_kernel(TapGemm p, Epi epi) {
-  constexpr int RK = BF16 ? 32 : MMA_BK;                  // k per barrier round
   __shared__ __align__(16) uint32_t As[2][MMA_BK][MMA_PITCH];
   __shared__ __align__(16) uint32_t Bs[2][MMA_BK][MMA_PITCH];
   __shared__ long long row_base[GBM];
@@ -72,68 +67,32 @@ __global__ void __launch_bounds__(256, 2) tap_gemm_mma_kernel(TapGemm p, Epi epi
     } else { row_s[tid] = -1; row_j[tid] = 0; row_base[tid] = 0; }
   }
   __syncthreads();
-  // per round and thread -- tf32: A row a_row, k = a_kq .. +3 and + 8; B k rows b_row and b_row + 8, columns b_col .. +3
-  //                         bf16: A row a_row, k = 16 (tid & 1) .. +15;  B k rows 4 b_row .. +3, columns b_col .. +3
-  constexpr int NV = BF16 ? 4 : 2;                        // float4 loads per operand, thread and round
-  const int a_row = tid >> 1, a_kq = (tid & 1) << 2;
-  const int b_row = tid >> 5, b_col = (tid & 31) << 2;
-  const int kt_per_tap = p.Kc / RK, n_kt = p.taps * kt_per_tap;
+  const int a_row = tid >> 1, a_kq = (tid & 1) << 2;       // A: row a_row, k = a_kq .. +3 and a_kq + 8 .. +11
+  const int b_row = tid >> 5, b_col = (tid & 31) << 2;    // B: k rows b_row and b_row + 8, columns b_col .. +3
+  const int kt_per_tap = p.Kc / MMA_BK, n_kt = p.taps * kt_per_tap;
   const int my_s = row_s[a_row], my_j = row_j[a_row];
   const long long my_base = row_base[a_row];
-  auto load_a = [&](int kt, float4 (&a)[NV]) {
-    const int tap = kt / kt_per_tap, c0 = (kt - tap * kt_per_tap) * RK;
+  auto load_a = [&](int kt, float4 (&a)[2]) {
+    const int tap = kt / kt_per_tap, c0 = (kt - tap * kt_per_tap) * MMA_BK;
     const int pos = my_j + tap - p.padL;
-    if (my_s < 0 || pos < 0 || pos >= p.Sin) {
-#pragma unroll
-      for (int h = 0; h < NV; ++h) a[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      return;
-    }
-    const float* src = p.A + my_base + (long long)pos * p.amap.pos_stride + c0;
-    if (BF16) {
-#pragma unroll
-      for (int h = 0; h < NV; ++h) a[h] = __ldg(reinterpret_cast<const float4*>(src + 16 * (tid & 1) + 4 * h));
-    } else {
-      a[0] = __ldg(reinterpret_cast<const float4*>(src + a_kq));
-      a[1] = __ldg(reinterpret_cast<const float4*>(src + a_kq + 8));
-    }
+    if (my_s < 0 || pos < 0 || pos >= p.Sin) { a[0] = a[1] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    const float* src = p.A + my_base + (long long)pos * p.amap.pos_stride + c0 + a_kq;
+    a[0] = __ldg(reinterpret_cast<const float4*>(src));
+    a[1] = __ldg(reinterpret_cast<const float4*>(src + 8));
   };
-  auto load_b = [&](int kt, float4 (&b)[NV]) {
+  auto load_b = [&](int kt, float4 (&b)[2]) {
     const int n = n0 + b_col;
-    if (n >= p.N) {
-#pragma unroll
-      for (int h = 0; h < NV; ++h) b[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      return;
-    }
-    if (BF16) {
-      const float* src = p.W + ((size_t)kt * RK + 4 * b_row) * p.N + n;
-#pragma unroll
-      for (int h = 0; h < NV; ++h) b[h] = __ldg(reinterpret_cast<const float4*>(src + (size_t)h * p.N));
-    } else {
-      const float* src = p.W + ((size_t)kt * RK + b_row) * p.N + n;
-      b[0] = __ldg(reinterpret_cast<const float4*>(src));
-      b[1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)8 * p.N));
-    }
+    if (n >= p.N) { b[0] = b[1] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    const float* src = p.W + ((size_t)kt * MMA_BK + b_row) * p.N + n;
+    b[0] = __ldg(reinterpret_cast<const float4*>(src));
+    b[1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)8 * p.N));
   };
-  auto stash = [&](int buf, const float4 (&a)[NV], const float4 (&b)[NV]) {
-    if (BF16) {
-      const int w0 = 8 * (tid & 1);                       // first k pair of this thread's 16 k
+  auto stash = [&](int buf, const float4 (&a)[2], const float4 (&b)[2]) {
 #pragma unroll
-      for (int h = 0; h < NV; ++h) {
-        As[buf][w0 + 2 * h][a_row] = pack2_bf16(a[h].x, a[h].y);
-        As[buf][w0 + 2 * h + 1][a_row] = pack2_bf16(a[h].z, a[h].w);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h)                           // k pair 2 b_row + h = rows 4 b_row + 2h, + 2h + 1
-        *reinterpret_cast<uint4*>(&Bs[buf][2 * b_row + h][b_col]) =
-            make_uint4(pack2_bf16(b[2 * h].x, b[2 * h + 1].x), pack2_bf16(b[2 * h].y, b[2 * h + 1].y),
-                       pack2_bf16(b[2 * h].z, b[2 * h + 1].z), pack2_bf16(b[2 * h].w, b[2 * h + 1].w));
-    } else {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        As[buf][8 * h + a_kq + 0][a_row] = to_tf32(a[h].x); As[buf][8 * h + a_kq + 1][a_row] = to_tf32(a[h].y);
-        As[buf][8 * h + a_kq + 2][a_row] = to_tf32(a[h].z); As[buf][8 * h + a_kq + 3][a_row] = to_tf32(a[h].w);
-        *reinterpret_cast<uint4*>(&Bs[buf][8 * h + b_row][b_col]) = make_uint4(to_tf32(b[h].x), to_tf32(b[h].y), to_tf32(b[h].z), to_tf32(b[h].w));
-      }
+    for (int h = 0; h < 2; ++h) {
+      As[buf][8 * h + a_kq + 0][a_row] = to_tf32(a[h].x); As[buf][8 * h + a_kq + 1][a_row] = to_tf32(a[h].y);
+      As[buf][8 * h + a_kq + 2][a_row] = to_tf32(a[h].z); As[buf][8 * h + a_kq + 3][a_row] = to_tf32(a[h].w);
+      *reinterpret_cast<uint4*>(&Bs[buf][8 * h + b_row][b_col]) = make_uint4(to_tf32(b[h].x), to_tf32(b[h].y), to_tf32(b[h].z), to_tf32(b[h].w));
     }
   };
   float acc[4][4][4];
@@ -143,7 +102,7 @@ __global__ void __launch_bounds__(256, 2) tap_gemm_mma_kernel(TapGemm p, Epi epi
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  float4 na[NV], nb[NV];
+  float4 na[2], nb[2];
   load_a(0, na); load_b(0, nb);
   stash(0, na, nb);
   __syncthreads();
@@ -151,8 +110,8 @@ __global__ void __launch_bounds__(256, 2) tap_gemm_mma_kernel(TapGemm p, Epi epi
     const int cur = kt & 1;
     const bool more = kt + 1 < n_kt;
     if (more) { load_a(kt + 1, na); load_b(kt + 1, nb); }
-    mma_warp_step<BF16>(&As[cur][0][0], &Bs[cur][0][0], acc, wm, wn, g, t);
-    mma_warp_step<BF16>(&As[cur][8][0], &Bs[cur][8][0], acc, wm, wn, g, t);
+    mma_warp_step(&As[cur][0][0], &Bs[cur][0][0], acc, wm, wn, g, t);
+    mma_warp_step(&As[cur][8][0], &Bs[cur][8][0], acc, wm, wn, g, t);
     if (more) stash(cur ^ 1, na, nb);
     __syncthreads();
   }
@@ -174,10 +133,7 @@ __global__ void __launch_bounds__(256, 2) tap_gemm_mma_kernel(TapGemm p, Epi epi
   }
 }
 
-template <bool BF16>
 __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
-  constexpr int RK = BF16 ? 32 : MMA_BK;                  // rows (the GEMM's k) per barrier round
-  constexpr int NV = BF16 ? 4 : 2;
   __shared__ __align__(16) uint32_t As[2][MMA_BK][MMA_PITCH];
   __shared__ __align__(16) uint32_t Bs[2][MMA_BK][MMA_PITCH];
   const int tid = threadIdx.x;
@@ -190,28 +146,26 @@ __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
   const long long r_lo = (long long)blockIdx.y * p.rows_per_split;
   const long long r_hi = r_lo + p.rows_per_split < p.R ? r_lo + p.rows_per_split : p.R;
   if (r_lo >= r_hi) return;
-  const int l_row = tid >> 5, l_col = (tid & 31) << 2;
-  // tf32: rows r0 + l_row and r0 + l_row + 8;  bf16: rows r0 + 4 l_row .. + 3 (two row PAIRS: words 2 l_row, 2 l_row + 1).
-  // The (sequence, position) of the thread's FIRST row is carried from round to round (the rows advance by RK): the 64-bit
-  // divisions of a per-load r / Sout and the SeqMap bases were most of this kernel's instructions (ncu r02: issue 52 %
-  // active against a tensor pipe at 17 %).
-  constexpr int RSTEP = BF16 ? 1 : 8;                     // distance between the thread's rows
-  long long row_first = r_lo + (BF16 ? 4 * l_row : l_row);
+  const int l_row = tid >> 5, l_col = (tid & 31) << 2;     // rows l_row and l_row + 8 of the round, columns l_col .. + 3
+  // The (sequence, position) of the thread's FIRST row is carried from round to round (the rows advance by MMA_BK): the
+  // 64-bit divisions of a per-load r / Sout and the SeqMap bases were most of this kernel's instructions (ncu r02: issue
+  // 52 % active against a tensor pipe at 17 %).
+  long long row_first = r_lo + l_row;
   int s_first = (int)(row_first / p.Sout), j_first = (int)(row_first - (long long)s_first * p.Sout);
   long long abase = p.amap.base(s_first), bbase = p.bmap.base(s_first);
   auto advance = [&]() {
-    row_first += RK; j_first += RK;
+    row_first += MMA_BK; j_first += MMA_BK;
     if (j_first >= p.Sout) {
       do { j_first -= p.Sout; ++s_first; } while (j_first >= p.Sout);
       abase = p.amap.base(s_first); bbase = p.bmap.base(s_first);
     }
   };
-  auto load = [&](float4 (&a)[NV], float4 (&b)[NV]) {     // the rows at the carried position
+  auto load = [&](float4 (&a)[2], float4 (&b)[2]) {
 #pragma unroll
-    for (int h = 0; h < NV; ++h) {
+    for (int h = 0; h < 2; ++h) {
       a[h] = make_float4(0.f, 0.f, 0.f, 0.f); b[h] = a[h];
-      if (row_first + h * RSTEP >= r_hi) continue;
-      int j = j_first + h * RSTEP;
+      if (row_first + 8 * h >= r_hi) continue;
+      int j = j_first + 8 * h;
       long long ab = abase, bb = bbase;
       if (j >= p.Sout) {                                    // this row belongs to a later sequence (rare)
         int sq = s_first;
@@ -225,23 +179,11 @@ __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
         b[h] = __ldg(reinterpret_cast<const float4*>(p.B + bb + (long long)j * p.bmap.pos_stride + n0 + l_col));
     }
   };
-  auto stash = [&](int buf, const float4 (&a)[NV], const float4 (&b)[NV]) {
-    if (BF16) {
+  auto stash = [&](int buf, const float4 (&a)[2], const float4 (&b)[2]) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        *reinterpret_cast<uint4*>(&As[buf][2 * l_row + h][l_col]) =
-            make_uint4(pack2_bf16(a[2 * h].x, a[2 * h + 1].x), pack2_bf16(a[2 * h].y, a[2 * h + 1].y),
-                       pack2_bf16(a[2 * h].z, a[2 * h + 1].z), pack2_bf16(a[2 * h].w, a[2 * h + 1].w));
-        *reinterpret_cast<uint4*>(&Bs[buf][2 * l_row + h][l_col]) =
-            make_uint4(pack2_bf16(b[2 * h].x, b[2 * h + 1].x), pack2_bf16(b[2 * h].y, b[2 * h + 1].y),
-                       pack2_bf16(b[2 * h].z, b[2 * h + 1].z), pack2_bf16(b[2 * h].w, b[2 * h + 1].w));
-      }
-    } else {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        *reinterpret_cast<uint4*>(&As[buf][l_row + 8 * h][l_col]) = make_uint4(to_tf32(a[h].x), to_tf32(a[h].y), to_tf32(a[h].z), to_tf32(a[h].w));
-        *reinterpret_cast<uint4*>(&Bs[buf][l_row + 8 * h][l_col]) = make_uint4(to_tf32(b[h].x), to_tf32(b[h].y), to_tf32(b[h].z), to_tf32(b[h].w));
-      }
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<uint4*>(&As[buf][l_row + 8 * h][l_col]) = make_uint4(to_tf32(a[h].x), to_tf32(a[h].y), to_tf32(a[h].z), to_tf32(a[h].w));
+      *reinterpret_cast<uint4*>(&Bs[buf][l_row + 8 * h][l_col]) = make_uint4(to_tf32(b[h].x), to_tf32(b[h].y), to_tf32(b[h].z), to_tf32(b[h].w));
     }
   };
   float acc[4][4][4];
@@ -251,16 +193,16 @@ __global__ void __launch_bounds__(256, 2) tap_wgrad_mma_kernel(TapWgrad p) {
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  float4 a[NV], b[NV];
+  float4 a[2], b[2];
   load(a, b);
   stash(0, a, b);
   __syncthreads();
   int cur = 0;
-  for (long long r0 = r_lo; r0 < r_hi; r0 += RK) {
-    const bool more = r0 + RK < r_hi;
+  for (long long r0 = r_lo; r0 < r_hi; r0 += MMA_BK) {
+    const bool more = r0 + MMA_BK < r_hi;
     if (more) { advance(); load(a, b); }
-    mma_warp_step<BF16>(&As[cur][0][0], &Bs[cur][0][0], acc, wm, wn, g, t);
-    mma_warp_step<BF16>(&As[cur][8][0], &Bs[cur][8][0], acc, wm, wn, g, t);
+    mma_warp_step(&As[cur][0][0], &Bs[cur][0][0], acc, wm, wn, g, t);
+    mma_warp_step(&As[cur][8][0], &Bs[cur][8][0], acc, wm, wn, g, t);
     if (more) stash(cur ^ 1, a, b);
     __syncthreads();
     cur ^= 1;

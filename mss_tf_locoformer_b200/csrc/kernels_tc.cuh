@@ -391,9 +391,6 @@ __global__ void __launch_bounds__(192 + 160 * NT, 1) ffn_tc_kernel(FfnTcParams p
     const int tp = threadIdx.x - 32 * (2 + NT);  // 0..127
     const int G = g.G, D = C / G;
     const float rs = rsqrtf((float)D);
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int m = quarter * 32 + lane;       // tile row in the final epilogue
-    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t slot = 0, ph = 0;
     // (code size matters: 16 warps run five different programs, and every unrolled copy of these bodies competes
     //  for the instruction cache -- ncu showed 'no instruction' as a top stall reason of the epilogue warps)

@@ -282,11 +282,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN2_THREADS, 1) ffn
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = g.C, H = g.H, KT = g.KT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS, NS = g.NS;
+  const int C = g.C, H = g.H, KT = g.KT, NC = g.NC, KS = g.KS, AR = g.AR, TS = g.TS;
   const int KH = g.KH, TPS = g.TPS;
   constexpr int NA = FFN2_NA;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t peer = rank ^ 1u;
   const uint32_t sbase = smem_u32(smem);
   float* tab_b1 = reinterpret_cast<float*>(smem + g.off_tab);
   float* tab_b2 = tab_b1 + 2 * H;

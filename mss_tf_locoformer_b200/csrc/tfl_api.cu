@@ -336,7 +336,7 @@ static int gemm_launch(const TapGemm& g, const Epi& epi, cudaStream_t st) {
   TFL_CHECK(g.Kc % GBK == 0 && g.N % 4 == 0, "tap-GEMM needs Kc %% 8 == 0 and N %% 4 == 0 (Kc %d N %d)", g.Kc, g.N);
   dim3 grid((unsigned)((g.M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
   if (g_gemm_mode == 2 && g.Kc % 32 == 0) tap_gemm_bf16_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
-  else if (g_gemm_mode != 0 && g.Kc % MMA_BK == 0) tap_gemm_mma_kernel<Epi, false><<<grid, 256, 0, st>>>(g, epi);
+  else if (g_gemm_mode != 0 && g.Kc % MMA_BK == 0) tap_gemm_mma_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
   else tap_gemm_kernel<Epi><<<grid, 256, 0, st>>>(g, epi);
   TFL_LAUNCH_CHECK();
   return 0;

@@ -131,7 +131,7 @@ static int wgrad_launch(TapWgrad g, int sm_count, cudaStream_t st) {
   g.rows_per_split = ((g.R + splits - 1) / splits + 31) / 32 * 32;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
   if (g_gemm_mode == 2) tap_wgrad_bf16_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
-  else if (g_gemm_mode == 1) tap_wgrad_mma_kernel<false><<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
+  else if (g_gemm_mode == 1) tap_wgrad_mma_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   else tap_wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 256, 0, st>>>(g);
   TFL_LAUNCH_CHECK();
   return 0;
