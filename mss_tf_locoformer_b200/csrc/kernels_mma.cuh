@@ -638,6 +638,216 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const float* __re
   }
 }
 
+// ---- bf16 forms of the two backward kernels (TFL_OPT_TRAIN_MODE 2): m16n8k16, the staged side as bf16 [row][HD + 8]
+// tiles read with ldmatrix (plain for the S / dP operands, transposed for the dQ / dK / dV operands) -- 12 (dq) and 16
+// (dk, dv) MMAs per 16 rows of the other side instead of 24 and 32, and the own-side fragments take half the registers.
+// P and dS are rounded to bf16 before their MMA (as in the forward tcgen05 kernel); accumulation stays fp32.
+template <int HD>
+__device__ __forceinline__ void stage_bf16_rows(__nv_bfloat16 (*tile)[HD + 8], const float* __restrict__ src, size_t row_stride,
+                                                int row0, int L, int hd, float mul) {
+  for (int e = threadIdx.x; e < 64 * (HD / 2); e += blockDim.x) {
+    const int rr = e / (HD / 2), d = 2 * (e - rr * (HD / 2));
+    float2 v = make_float2(0.f, 0.f);
+    if (row0 + rr < L && d < hd) v = *reinterpret_cast<const float2*>(src + (size_t)(row0 + rr) * row_stride + d);
+    *reinterpret_cast<uint32_t*>(&tile[rr][d]) = pack2_bf16(v.x * mul, v.y * mul);
+  }
+}
+// own-side A fragments (16 rows x HD) from fp32 rows r0 / r1: [ks][0..3] = (r0, 2t), (r1, 2t), (r0, 2t + 8), (r1, 2t + 8) pairs
+template <int HD>
+__device__ __forceinline__ void load_a_rows_bf16(uint32_t (&a)[HD / 16][4], const float* __restrict__ src, size_t row_stride,
+                                                 int r0, int r1, int L, int hd, int t, float mul) {
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = (e & 1) ? r1 : r0, d = 16 * ks + 2 * t + ((e & 2) ? 8 : 0);
+      float2 v = make_float2(0.f, 0.f);
+      if (r < L && d < hd) v = *reinterpret_cast<const float2*>(src + (size_t)r * row_stride + d);
+      a[ks][e] = pack2_bf16(v.x * mul, v.y * mul);
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_bwd_dq_bf16_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                               const float* __restrict__ v, const float* __restrict__ o,
+                                                               const float* __restrict__ dO, const float* __restrict__ lse,
+                                                               float* __restrict__ dq, float* __restrict__ Dbuf,
+                                                               int L, int hd, int heads, float scale) {
+  constexpr int TK = 64, KS = HD / 16, NT = HD / 8;
+  __shared__ __align__(16) __nv_bfloat16 ks_[TK][HD + 8], vs_[TK][HD + 8];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16 + g, r1 = r0 + 8;
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  const size_t A = (size_t)heads * hd;
+  const float* dO_h = dO + (size_t)s * L * A + (size_t)head * hd;     // row stride A
+  const float* o_h = o + (size_t)s * L * A + (size_t)head * hd;
+  uint32_t aq[KS][4], ado[KS][4];
+  load_a_rows_bf16<HD>(aq, q + base, hd, r0, r1, L, hd, t, scale);
+  load_a_rows_bf16<HD>(ado, dO_h, A, r0, r1, L, hd, t, 1.f);
+  float D0 = 0.f, D1 = 0.f;                                             // D = dO . O from the fp32 values
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = (e & 1) ? r1 : r0, d = 16 * ks + 2 * t + ((e & 2) ? 8 : 0);
+      if (r < L && d < hd) {
+        const float2 gv = *reinterpret_cast<const float2*>(dO_h + (size_t)r * A + d);
+        const float2 ov = *reinterpret_cast<const float2*>(o_h + (size_t)r * A + d);
+        const float dd = gv.x * ov.x + gv.y * ov.y;
+        if (e & 1) D1 += dd; else D0 += dd;
+      }
+    }
+  D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+  D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+  const size_t lrow = ((size_t)s * heads + head) * L;
+  const float l0 = r0 < L ? lse[lrow + r0] : 0.f, l1 = r1 < L ? lse[lrow + r1] : 0.f;
+  if (t == 0) {
+    if (r0 < L) Dbuf[lrow + r0] = D0;
+    if (r1 < L) Dbuf[lrow + r1] = D1;
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int j0 = 0; j0 < L; j0 += TK) {
+    __syncthreads();
+    stage_bf16_rows<HD>(ks_, k + base, hd, j0, L, hd, 1.f);
+    stage_bf16_rows<HD>(vs_, v + base, hd, j0, L, hd, 1.f);
+    __syncthreads();
+#pragma unroll 2
+    for (int kb = 0; kb < TK / 16; ++kb) {
+      const int key0 = kb * 16;
+      if (j0 + key0 >= L) break;
+      float S[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dP[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {   // matrices (keys 0-7 | 8-15) x (dims 16 ks .. +7 | +8 .. +15): b0, b1 of n-tile 0 then of n-tile 1
+        uint32_t bk[4], bv[4];
+        ldmatrix_x4(bk, &ks_[key0 + (lane & 7) + 8 * (lane >> 4)][16 * ks + 8 * ((lane >> 3) & 1)]);
+        ldmatrix_x4(bv, &vs_[key0 + (lane & 7) + 8 * (lane >> 4)][16 * ks + 8 * ((lane >> 3) & 1)]);
+        const uint32_t bk0[2] = {bk[0], bk[1]}, bk1[2] = {bk[2], bk[3]}, bv0[2] = {bv[0], bv[1]}, bv1[2] = {bv[2], bv[3]};
+        mma_bf16(S[0], aq[ks], bk0); mma_bf16(S[1], aq[ks], bk1);
+        mma_bf16(dP[0], ado[ks], bv0); mma_bf16(dP[1], ado[ks], bv1);
+      }
+      float ds[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const bool v0 = j0 + key0 + 8 * n + 2 * t < L, v1 = j0 + key0 + 8 * n + 2 * t + 1 < L;
+        ds[n][0] = v0 ? __expf(S[n][0] - l0) * (dP[n][0] - D0) : 0.f;
+        ds[n][1] = v1 ? __expf(S[n][1] - l0) * (dP[n][1] - D0) : 0.f;
+        ds[n][2] = v0 ? __expf(S[n][2] - l1) * (dP[n][2] - D1) : 0.f;
+        ds[n][3] = v1 ? __expf(S[n][3] - l1) * (dP[n][3] - D1) : 0.f;
+      }
+      const uint32_t ads[4] = {pack2_bf16(ds[0][0], ds[0][1]), pack2_bf16(ds[0][2], ds[0][3]),
+                               pack2_bf16(ds[1][0], ds[1][1]), pack2_bf16(ds[1][2], ds[1][3])};
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {   // K^T operand: matrices (keys 0-7 | 8-15) x (dims 16 jp .. +7 | +8 .. +15), transposed
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, &ks_[key0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+        const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+        mma_bf16(acc[2 * jp], ads, b0); mma_bf16(acc[2 * jp + 1], ads, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int d = 8 * j + 2 * t;
+    if (d < hd) {
+      if (r0 < L) *reinterpret_cast<float2*>(dq + base + (size_t)r0 * hd + d) = make_float2(acc[j][0] * scale, acc[j][1] * scale);
+      if (r1 < L) *reinterpret_cast<float2*>(dq + base + (size_t)r1 * hd + d) = make_float2(acc[j][2] * scale, acc[j][3] * scale);
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_bwd_dkv_bf16_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                const float* __restrict__ v, const float* __restrict__ dO,
+                                                                const float* __restrict__ lse, const float* __restrict__ Dbuf,
+                                                                float* __restrict__ dk, float* __restrict__ dv,
+                                                                int L, int hd, int heads, float scale) {
+  constexpr int TQ = 64, KS = HD / 16, NT = HD / 8;
+  __shared__ __align__(16) __nv_bfloat16 qs_[TQ][HD + 8], dos_[TQ][HD + 8];
+  __shared__ float ls_[TQ], Ds_[TQ];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16 + g, r1 = r0 + 8;          // this lane's two key rows
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  const size_t A = (size_t)heads * hd;
+  const size_t lrow = ((size_t)s * heads + head) * L;
+  const float* dO_h = dO + (size_t)s * L * A + (size_t)head * hd;
+  uint32_t ak[KS][4], av[KS][4];
+  load_a_rows_bf16<HD>(ak, k + base, hd, r0, r1, L, hd, t, 1.f);
+  load_a_rows_bf16<HD>(av, v + base, hd, r0, r1, L, hd, t, 1.f);
+  float dK[NT][4], dV[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    dK[j][0] = dK[j][1] = dK[j][2] = dK[j][3] = 0.f;
+    dV[j][0] = dV[j][1] = dV[j][2] = dV[j][3] = 0.f;
+  }
+  for (int i0 = 0; i0 < L; i0 += TQ) {
+    __syncthreads();
+    stage_bf16_rows<HD>(qs_, q + base, hd, i0, L, hd, scale);
+    stage_bf16_rows<HD>(dos_, dO_h, A, i0, L, hd, 1.f);
+    for (int e = threadIdx.x; e < TQ; e += blockDim.x) {
+      const bool ok = i0 + e < L;
+      ls_[e] = ok ? lse[lrow + i0 + e] : INFINITY;                       // exp(S - inf) = 0: queries beyond the sequence
+      Ds_[e] = ok ? Dbuf[lrow + i0 + e] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int qb = 0; qb < TQ / 16; ++qb) {
+      const int qq0 = qb * 16;
+      if (i0 + qq0 >= L) break;
+      float ST[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dPT[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bq[4], bd[4];
+        ldmatrix_x4(bq, &qs_[qq0 + (lane & 7) + 8 * (lane >> 4)][16 * ks + 8 * ((lane >> 3) & 1)]);
+        ldmatrix_x4(bd, &dos_[qq0 + (lane & 7) + 8 * (lane >> 4)][16 * ks + 8 * ((lane >> 3) & 1)]);
+        const uint32_t bq0[2] = {bq[0], bq[1]}, bq1[2] = {bq[2], bq[3]}, bd0[2] = {bd[0], bd[1]}, bd1[2] = {bd[2], bd[3]};
+        mma_bf16(ST[0], ak[ks], bq0); mma_bf16(ST[1], ak[ks], bq1);
+        mma_bf16(dPT[0], av[ks], bd0); mma_bf16(dPT[1], av[ks], bd1);
+      }
+      float pt[2][4], ds[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int c = qq0 + 8 * n + 2 * t;
+        const float la = ls_[c], lb = ls_[c + 1], da = Ds_[c], db = Ds_[c + 1];
+        pt[n][0] = __expf(ST[n][0] - la); pt[n][1] = __expf(ST[n][1] - lb);
+        pt[n][2] = __expf(ST[n][2] - la); pt[n][3] = __expf(ST[n][3] - lb);
+        ds[n][0] = pt[n][0] * (dPT[n][0] - da); ds[n][1] = pt[n][1] * (dPT[n][1] - db);
+        ds[n][2] = pt[n][2] * (dPT[n][2] - da); ds[n][3] = pt[n][3] * (dPT[n][3] - db);
+      }
+      const uint32_t ap[4] = {pack2_bf16(pt[0][0], pt[0][1]), pack2_bf16(pt[0][2], pt[0][3]),
+                              pack2_bf16(pt[1][0], pt[1][1]), pack2_bf16(pt[1][2], pt[1][3])};
+      const uint32_t ads[4] = {pack2_bf16(ds[0][0], ds[0][1]), pack2_bf16(ds[0][2], ds[0][3]),
+                               pack2_bf16(ds[1][0], ds[1][1]), pack2_bf16(ds[1][2], ds[1][3])};
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        uint32_t bo[4], bq[4];
+        ldmatrix_x4_trans(bo, &dos_[qq0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+        ldmatrix_x4_trans(bq, &qs_[qq0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+        const uint32_t bo0[2] = {bo[0], bo[1]}, bo1[2] = {bo[2], bo[3]}, bq0[2] = {bq[0], bq[1]}, bq1[2] = {bq[2], bq[3]};
+        mma_bf16(dV[2 * jp], ap, bo0); mma_bf16(dV[2 * jp + 1], ap, bo1);
+        mma_bf16(dK[2 * jp], ads, bq0); mma_bf16(dK[2 * jp + 1], ads, bq1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int d = 8 * j + 2 * t;
+    if (d < hd) {   // qs_ carries the softmax scale already: dK_j = sum_i dS_ij * (scale * Q_i)
+      if (r0 < L) {
+        *reinterpret_cast<float2*>(dk + base + (size_t)r0 * hd + d) = make_float2(dK[j][0], dK[j][1]);
+        *reinterpret_cast<float2*>(dv + base + (size_t)r0 * hd + d) = make_float2(dV[j][0], dV[j][1]);
+      }
+      if (r1 < L) {
+        *reinterpret_cast<float2*>(dk + base + (size_t)r1 * hd + d) = make_float2(dK[j][2], dK[j][3]);
+        *reinterpret_cast<float2*>(dv + base + (size_t)r1 * hd + d) = make_float2(dV[j][2], dV[j][3]);
+      }
+    }
+  }
+}
+
 // Forward attention with the log-sum-exp kept (training forward in TFL_OPT_TRAIN_MODE 1 and the recompute of the backward
 // pass): the mma form of attn_f32_kernel.  16 queries per warp, 64 keys per stage; S of the whole stage first (8 tiles),
 // one online-softmax update per stage, then P V with the accumulator-as-A-fragment trick above.

@@ -281,7 +281,15 @@ static int attn_backward(const tfl_plan* pl, const char* packed, int layer, int 
   const float scale = 1.0f / sqrtf((float)hd);
   if (g_gemm_tf32 && hd % 2 == 0 && hd > 8 && hd <= 32) {   // tensor-core form (tf32 mma.sync), 64 rows per block
     dim3 grid64((L + 63) / 64, heads, nseq);
-    if (hd <= 16) {
+    if (g_gemm_mode == 2 && hd <= 16) {
+      attn_bwd_dq_bf16_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, dO, lse, dqkv_h, Dbuf, L, hd, heads, scale);
+      TFL_LAUNCH_CHECK();
+      attn_bwd_dkv_bf16_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, dO, lse, Dbuf, dqkv_h + per, dqkv_h + 2 * per, L, hd, heads, scale);
+    } else if (g_gemm_mode == 2) {
+      attn_bwd_dq_bf16_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, dO, lse, dqkv_h, Dbuf, L, hd, heads, scale);
+      TFL_LAUNCH_CHECK();
+      attn_bwd_dkv_bf16_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, dO, lse, Dbuf, dqkv_h + per, dqkv_h + 2 * per, L, hd, heads, scale);
+    } else if (hd <= 16) {
       attn_bwd_dq_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, dO, lse, dqkv_h, Dbuf, L, hd, heads, scale);
       TFL_LAUNCH_CHECK();
       attn_bwd_dkv_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, dO, lse, Dbuf, dqkv_h + per, dqkv_h + 2 * per, L, hd, heads, scale);

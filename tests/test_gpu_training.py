@@ -31,10 +31,11 @@ def pkg():
 MODES = {"fp32": 0, "tf32": 1, "mixed": 2}
 
 
-@pytest.fixture(params=["fp32", "tf32"])
+@pytest.fixture(params=["fp32", "tf32", "mixed"])
 def gemm_mode(request, pkg):
-    """TFL_OPT_TRAIN_MODE of the sub-block tests: exact fp32 on CUDA cores (parity mode, tight tolerances) or mma.sync tf32
-    GEMMs with fp32 accumulation (2^-11 per operand, tolerances ~20x wider)."""
+    """TFL_OPT_TRAIN_MODE of the sub-block tests: exact fp32 on CUDA cores (parity mode, tight tolerances), mma.sync tf32
+    GEMMs / attention with fp32 accumulation (2^-11 per operand, tolerances ~20x wider), or the bf16 mma.sync forms of the
+    mixed mode (2^-9 per operand; the sub-block entry points have no forward of their own, so "mixed" here = bf16 backward)."""
     from mss_tf_locoformer_b200 import _lib
     lib = _lib.load()
     assert lib.tfl_debug_set_option(5, MODES[request.param]) == 0
@@ -55,7 +56,7 @@ def train_mode(request, pkg):
 
 # (step: deconv.bias is a sum of terms that largely cancel -- 2.5e-3 against float64 in fp32 mode, everything else < 2e-5)
 TOL = {"fp32": dict(dx=1e-4, grad=1e-3, step=5e-3, loss=2e-4), "tf32": dict(dx=5e-3, grad=2e-2, step=3e-2, loss=3e-3),
-       "mixed": dict(step=3e-2, loss=3e-3)}
+       "mixed": dict(dx=2e-2, grad=3e-2, step=3e-2, loss=3e-3)}
 
 
 def _rel(got, want):
