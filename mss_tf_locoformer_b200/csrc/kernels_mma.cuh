@@ -848,6 +848,99 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_bf16_kernel(const float* __r
   }
 }
 
+// bf16 form of the forward-with-lse kernel below (the backward pass's recompute in mode 2): 64 keys per stage, S of the
+// whole stage first (8 n-tiles = 4 ldmatrix.x4 per 16 dims), one online-softmax update per stage, P V with V read transposed.
+template <int HD>
+__global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                            const float* __restrict__ v, float* __restrict__ o,
+                                                            int L, int hd, int heads, float scale, float* __restrict__ lse) {
+  constexpr int TK = 64, KS = HD / 16, NT = HD / 8;
+  __shared__ __align__(16) __nv_bfloat16 ks_[TK][HD + 8], vs_[TK][HD + 8];
+  const int head = blockIdx.y, s = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16 + g, r1 = r0 + 8;
+  const size_t base = ((size_t)s * heads + head) * (size_t)L * hd;
+  const size_t A = (size_t)heads * hd;
+  uint32_t aq[KS][4];
+  load_a_rows_bf16<HD>(aq, q + base, hd, r0, r1, L, hd, t, scale);
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int j0 = 0; j0 < L; j0 += TK) {
+    __syncthreads();
+    stage_bf16_rows<HD>(ks_, k + base, hd, j0, L, hd, 1.f);
+    stage_bf16_rows<HD>(vs_, v + base, hd, j0, L, hd, 1.f);
+    __syncthreads();
+    float S[TK / 8][4];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int kb = 0; kb < TK / 16; ++kb) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) S[2 * kb + n][0] = S[2 * kb + n][1] = S[2 * kb + n][2] = S[2 * kb + n][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bk[4];
+        ldmatrix_x4(bk, &ks_[kb * 16 + (lane & 7) + 8 * (lane >> 4)][16 * ks + 8 * ((lane >> 3) & 1)]);
+        const uint32_t b0[2] = {bk[0], bk[1]}, b1[2] = {bk[2], bk[3]};
+        mma_bf16(S[2 * kb], aq[ks], b0); mma_bf16(S[2 * kb + 1], aq[ks], b1);
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int nt = 2 * kb + n, c0 = j0 + nt * 8 + 2 * t;
+        if (c0 >= L) { S[nt][0] = -INFINITY; S[nt][2] = -INFINITY; }
+        if (c0 + 1 >= L) { S[nt][1] = -INFINITY; S[nt][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);        // finite: every stage holds at least one key < L
+    const float a0 = __expf(m0 - n0), a1 = __expf(m1 - n1);
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[j][0] *= a0; acc[j][1] *= a0; acc[j][2] *= a1; acc[j][3] *= a1; }
+    m0 = n0; m1 = n1;
+#pragma unroll
+    for (int kb = 0; kb < TK / 16; ++kb) {
+      float pr[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int nt = 2 * kb + n;
+        pr[n][0] = __expf(S[nt][0] - n0); pr[n][1] = __expf(S[nt][1] - n0);
+        pr[n][2] = __expf(S[nt][2] - n1); pr[n][3] = __expf(S[nt][3] - n1);
+        l0 += pr[n][0] + pr[n][1]; l1 += pr[n][2] + pr[n][3];
+      }
+      const uint32_t ap[4] = {pack2_bf16(pr[0][0], pr[0][1]), pack2_bf16(pr[0][2], pr[0][3]),
+                              pack2_bf16(pr[1][0], pr[1][1]), pack2_bf16(pr[1][2], pr[1][3])};
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, &vs_[kb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+        const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+        mma_bf16(acc[2 * jp], ap, b0); mma_bf16(acc[2 * jp + 1], ap, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int d = 8 * j + 2 * t;
+    if (d < hd) {
+      if (r0 < L) *reinterpret_cast<float2*>(o + ((size_t)s * L + r0) * A + (size_t)head * hd + d) = make_float2(acc[j][0] * i0, acc[j][1] * i0);
+      if (r1 < L) *reinterpret_cast<float2*>(o + ((size_t)s * L + r1) * A + (size_t)head * hd + d) = make_float2(acc[j][2] * i1, acc[j][3] * i1);
+    }
+  }
+  if (lse != nullptr && t == 0) {
+    const size_t lrow = ((size_t)s * heads + head) * L;
+    if (r0 < L) lse[lrow + r0] = m0 + logf(l0);
+    if (r1 < L) lse[lrow + r1] = m1 + logf(l1);
+  }
+}
+
 // Forward attention with the log-sum-exp kept (training forward in TFL_OPT_TRAIN_MODE 1 and the recompute of the backward
 // pass): the mma form of attn_f32_kernel.  16 queries per warp, 64 keys per stage; S of the whole stage first (8 tiles),
 // one online-softmax update per stage, then P V with the accumulator-as-A-fragment trick above.

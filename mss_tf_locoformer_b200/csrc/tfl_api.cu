@@ -388,7 +388,9 @@ static int attn_f32(const tfl_plan* pl, const char* packed, int layer, int axis,
   const float scale = 1.0f / sqrtf((float)hd);
   if (g_gemm_tf32 && hd % 2 == 0 && hd > 8 && hd <= 32) {   // training modes >= 1: tf32 mma.sync form (kernels_mma.cuh)
     dim3 grid64((L + 63) / 64, heads, nseq);
-    if (hd <= 16) attn_fwd_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
+    if (g_gemm_mode == 2 && hd <= 16) attn_fwd_bf16_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
+    else if (g_gemm_mode == 2) attn_fwd_bf16_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
+    else if (hd <= 16) attn_fwd_mma_kernel<16><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
     else attn_fwd_mma_kernel<32><<<grid64, 128, 0, st>>>(qkv, qkv + per, qkv + 2 * per, o, L, hd, heads, scale, lse);
   } else {
   dim3 grid((L + 127) / 128, heads, nseq);
