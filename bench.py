@@ -79,6 +79,14 @@ def ffn_call_flops(cfg, batch, n_samples, axis, hidden):
     return 6 * K * C * hidden * rows
 
 
+def workload_config(variant, batch):
+    """The `config` object of the forward bench line: a static description of the workload, identical for the b200 arm
+    and the --impl reference arm (whose bounded sample of it is stated in `cpu_baseline.sample`); measured figures go
+    under `derived`, never here."""
+    return {"workload": WORKLOADS[variant], "batch_per_gpu": batch, "segment_samples": SEG,
+            "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
 def make_mixture(batch, n_samples, seed=1234):
     g = torch.Generator().manual_seed(seed)
     t = torch.arange(n_samples) / SR
@@ -201,7 +209,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.variant], "sample": sample},
+        "config": workload_config(args.variant, args.batch),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -606,17 +614,15 @@ def main():
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.variant], "batch_per_gpu": B, "segment_samples": SEG,
-                   "precision": args.precision,
-                   "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-                   "x_realtime_per_gpu": value / world},
+        "config": workload_config(args.variant, B),
+        "derived": {"x_realtime_per_gpu": value / world},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": world * mix_host.numel() * 4,
                 "d2h_bytes_per_step": world * out_host.numel() * 4},
         "gpu_launches": int(launches) * world,
         "clocks": clocks.summary(),
     }
     fl = algorithmic_flops(cfg, B, SEG)
-    line["config"]["tflops_total_algorithmic"] = fl["total"] * world * args.steps / (ms / 1e3) / 1e12
+    line["derived"]["tflops_total_algorithmic"] = fl["total"] * world * args.steps / (ms / 1e3) / 1e12
     # ---- roofline of the dominant kernel: the ConvSwiGLU FFN (83 % of FLOPs), frequency axis ----
     peaks = {}
     try:
@@ -628,7 +634,7 @@ def main():
     peak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained", 1400.0))
     peak_sustained = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.4 PF"
-    line["config"]["step_frac_of_sustained_bf16_peak"] = line["config"]["tflops_total_algorithmic"] / peak_sustained
+    line["derived"]["step_frac_of_sustained_bf16_peak"] = line["derived"]["tflops_total_algorithmic"] / peak_sustained
     eng = model._ready()
     prec = 1 if args.precision == "bf16" else 0
     Tf, F = 1 + SEG // cfg["hop_length"], cfg["n_fft"] // 2 + 1
