@@ -99,6 +99,10 @@ int tfl_rope_attn(const tfl_plan* plan, const void* packed, int layer, int axis,
 /* :182, :229-237.  x [B, Tf, F, C] -> est [B, S, Tf, F, 2] (complex64 [B, S, Tf, F]). */
 int tfl_dec_conv(const tfl_plan* plan, const void* packed, const float* x, int batch, int n_frames,
                  int n_freq, float* est, tfl_stream_t stream);
+/* The same stage in the arithmetic of `precision`: TFL_PRECISION_FP32 = tfl_dec_conv; TFL_PRECISION_BF16 = the tf32
+ * mma.sync decoder that tfl_forward / tfl_separator_forward run in bf16 mode (operands rounded to tf32, fp32 sums). */
+int tfl_dec_conv_mode(const tfl_plan* plan, const void* packed, const float* x, int batch, int n_frames,
+                      int n_freq, float* est, int precision, tfl_stream_t stream);
 /* :56-75, :239-250.  est [B, S, Tf, F, 2] -> audio [S, B, n_samples] (all sources, one launch). */
 int tfl_istft_ola(const tfl_plan* plan, const void* packed, const float* est, int batch, int n_frames,
                   int n_samples, float* audio, tfl_stream_t stream);
@@ -196,9 +200,12 @@ int tfl_bs_band_decode(const float* x, const float* spec, int batch, int n_chan,
  *                        1 = every GEMM as mma.sync tf32 operands with fp32 accumulation; 2 (default) = 1 + the FORWARD
  *                        pass of the sub-blocks on the bf16 tcgen05 kernels of the inference path (the reference trains
  *                        with `tf32: true` under bf16 autocast); the backward pass recomputes on the tf32 path
+ *   TFL_OPT_DEC_KERNEL   bf16-mode decoder: 1 = dec_conv_mma_kernel (9-tap gather), 2 = dec_conv_scatter_kernel (every
+ *                        input row read once, rolling output-frame accumulators in shared memory; default for
+ *                        emb_dim in {32, 64, 96, 128})
  *   TFL_OPT_TRACE_BASE   first chunk / tile index the pipeline trace records (64 entries per event; default 0) */
 enum { TFL_OPT_ATTN_KERNEL = 0, TFL_OPT_FFN_KERNEL = 1, TFL_OPT_TRACE_BASE = 2, TFL_OPT_TAIL_KERNEL = 3, TFL_OPT_PDL = 4,
-       TFL_OPT_TRAIN_MODE = 5, TFL_OPT_COUNT = 8 };
+       TFL_OPT_TRAIN_MODE = 5, TFL_OPT_DEC_KERNEL = 6, TFL_OPT_COUNT = 8 };
 int tfl_debug_set_option(int key, int value);
 
 /* Diagnostic: install (or clear with NULL) a device buffer of >= 16 * 64 uint64 in which block 0 of the tcgen05 FFN

@@ -41,6 +41,7 @@ SIGNATURES = {  # name -> (restype, argtypes); must list every symbol of include
     "tfl_conv_swiglu_ffn_out": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "tfl_rope_attn": (_I, [_P, _P, _I, _I, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "tfl_dec_conv": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "tfl_dec_conv_mode": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _P]),
     "tfl_istft_ola": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "tfl_blocks": (_I, [_P, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "tfl_forward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),

@@ -783,6 +783,147 @@ __global__ void __launch_bounds__(256) dec_conv_mma_kernel(const float* __restri
 }
 
 // --------------------------------------------------------------------------------------
+// K6 (bf16 mode, C in {32, 64, 96, 128}) decoder in SCATTER form: every input position is read from HBM exactly once.
+// A transposed conv is a scatter: position (ti, fi) sends P[(dt, df, o)] = W[tap = dt*3+df][o] . x[ti, fi, :] to
+// output (ti - 1 + dt, fi - 1 + df, o).  P is one GEMM with M = positions, N = 72 (9 taps x 8 outputs), K = C:
+// the same 144 mma.sync m16n8k8 (tf32) per 16 positions as the gather kernel above, but 16 instead of 144 128-bit
+// global loads per thread -- the gather kernel fetched every x row for each of the 9 taps (L1 / L2 line lookups
+// bound it at 0.97 ms for 1.09 GB).
+// A block owns a strip of <= 126 output bins (128 input bins, one 16-bin tile per warp) and a run of output frames
+// [ta, tb); it walks the input frames ta-1 .. tb in order and adds every warp's P into three rolling output-frame
+// accumulators in shared memory ([frame % 3][source][bin], initialised to the bias).  One pass per frequency tap df
+// (the three time taps of a pass land in different frames, so all targets of a pass are distinct; __syncthreads
+// between passes), so the summation order of every output is fixed: input frames ascending, df ascending --
+// deterministic and independent of the batch index and of how frames / bins were split into runs / strips.  After
+// input frame ti the output frame ti - 1 is complete: written out ([B, S, Tf, F, 2], 8 bytes per lane, contiguous
+// per source) and its accumulator reset.
+// x rows are prefetched one frame ahead in 32-channel chunks (register ring of NCH = C / 32 chunks, refilled chunk
+// by chunk as the MMAs consume them): 3/4 of a 16-bin tile (6 KB) is in flight per warp at any time.
+// wd layout: [9 taps][8 outputs][C] as above; shared copy [72][C + 16] (the 16-word pad makes the 128-bit B-fragment
+// loads of a quarter warp conflict-free).
+// --------------------------------------------------------------------------------------
+constexpr int DEC_WB = 132;   // accumulator bins per (frame, source): 130 used; 2 * DEC_WB % 32 == 8 keeps the RMW conflict-free
+constexpr int DEC_WOUT = 126; // complete output bins of a 128-bin input strip
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) dec_conv_scatter_kernel(const float* __restrict__ x, int n_batch, int n_frames,
+                                                                  int n_freq, int n_out, const float* __restrict__ wd,
+                                                                  const float* __restrict__ bias, float* __restrict__ est,
+                                                                  int NS, int WOUT, int NR, int R) {
+  constexpr int C = 32 * NCH, WS = C + 16;
+  extern __shared__ float dsm[];
+  float* wsm = dsm;                                            // [72][WS] tf32
+  float2* accs = reinterpret_cast<float2*>(dsm + 72 * WS);     // [3][4][DEC_WB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n_src = n_out >> 1;
+  for (int i = tid; i < 72 * C; i += 256) wsm[(i / C) * WS + (i % C)] = __uint_as_float(to_tf32(wd[i]));
+  // flush / reset mapping: thread (source fs, j) owns accumulator bins 2 + j and 66 + j (+ one of the four unused edge bins)
+  const int fs = tid >> 6, fj = tid & 63;
+  const float2 fbias = make_float2(2 * fs < n_out ? __ldg(&bias[2 * fs]) : 0.f, 2 * fs + 1 < n_out ? __ldg(&bias[2 * fs + 1]) : 0.f);
+  for (int sl = 0; sl < 3; ++sl) {
+    float2* a = accs + (sl * 4 + fs) * DEC_WB;
+    a[2 + fj] = fbias; a[66 + fj] = fbias;
+    if (fj < 4) a[fj < 2 ? fj : 128 + fj] = fbias;
+  }
+  __syncthreads();
+  const long long n_items = (long long)n_batch * NS * NR;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int run = (int)(item % NR), strip = (int)((item / NR) % NS), b = (int)(item / ((long long)NR * NS));
+    const int ta = run * R, tb = min(ta + R, n_frames);
+    if (ta >= n_frames) continue;
+    const int o0 = strip * WOUT, wout = min(WOUT, n_freq - o0), i0 = o0 - 1;   // input bins i0 .. i0 + wout + 1
+    if (wout <= 0) continue;
+    const int ra = 16 * warp + g, rb = ra + 8;                 // tile rows of this lane; accumulator bin = row + df
+    const int fa = i0 + ra, fb = i0 + rb;
+    const bool va = fa >= 0 && fa < n_freq && ra < wout + 2, vb = fb >= 0 && fb < n_freq && rb < wout + 2;
+    const bool active = 16 * warp < wout + 2 && i0 + 16 * warp < n_freq;      // warp-uniform
+    const int t_first = max(ta - 1, 0), t_last = min(tb, n_frames - 1);
+    const float* xa0 = x + (((size_t)b * n_frames) * n_freq + (va ? fa : 0)) * C + 4 * t4;
+    const float* xb0 = x + (((size_t)b * n_frames) * n_freq + (vb ? fb : 0)) * C + 4 * t4;
+    const size_t fstride = (size_t)n_freq * C;
+    float4 X[NCH][4];                                          // [chunk][row a: 2 steps of 16 channels, row b: 2 steps]
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld_chunk = [&](int j, int ti) {
+      const float* pa = xa0 + (size_t)ti * fstride + 32 * j;
+      const float* pb = xb0 + (size_t)ti * fstride + 32 * j;
+      X[j][0] = va ? __ldg(reinterpret_cast<const float4*>(pa)) : z4;
+      X[j][1] = va ? __ldg(reinterpret_cast<const float4*>(pa + 16)) : z4;
+      X[j][2] = vb ? __ldg(reinterpret_cast<const float4*>(pb)) : z4;
+      X[j][3] = vb ? __ldg(reinterpret_cast<const float4*>(pb + 16)) : z4;
+    };
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) ld_chunk(j, t_first);
+    }
+    for (int ti = t_first; ti <= t_last; ++ti) {
+      bool use[3];                                             // output frame ti - 1 + dt belongs to this run
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) use[dt] = ti - 1 + dt >= ta && ti - 1 + dt < tb;
+      float acc[9][4];
+#pragma unroll
+      for (int nt = 0; nt < 9; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const float4 xa = X[j][s], xb = X[j][2 + s];
+            const uint32_t a0 = to_tf32(xa.x), a1 = to_tf32(xb.x), a2 = to_tf32(xa.y), a3 = to_tf32(xb.y);
+            const uint32_t c0 = to_tf32(xa.z), c1 = to_tf32(xb.z), c2 = to_tf32(xa.w), c3 = to_tf32(xb.w);
+            const float* pw = wsm + g * WS + 32 * j + 16 * s + 4 * t4;
+#pragma unroll
+            for (int nt = 0; nt < 9; ++nt) {
+              if (use[nt / 3]) {
+                const float4 w = *reinterpret_cast<const float4*>(pw + nt * 8 * WS);
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(__float_as_uint(w.x)), "r"(__float_as_uint(w.y)));
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(__float_as_uint(w.z)), "r"(__float_as_uint(w.w)));
+              }
+            }
+          }
+          if (ti < t_last) ld_chunk(j, ti + 1);                // refill the chunk just consumed with the next input frame
+        }
+      }
+      // scatter: one pass per frequency tap; within a pass every (frame, source, bin) target is distinct
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        if (active) {
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt) {
+            if (use[dt]) {
+              float2* a = accs + (((ti + 2 + dt) % 3) * 4 + t4) * DEC_WB + df;   // frame ti - 1 + dt, source t4
+              float2 u = a[ra], v = a[rb];
+              u.x += acc[dt * 3 + df][0]; u.y += acc[dt * 3 + df][1];
+              v.x += acc[dt * 3 + df][2]; v.y += acc[dt * 3 + df][3];
+              a[ra] = u; a[rb] = v;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // output frame ti - 1 is complete (and output frame n_frames - 1 after the last input frame)
+      for (int to = ti - 1; to <= (ti == n_frames - 1 ? ti : ti - 1); ++to) {
+        if (to < ta || to >= tb) continue;
+        float2* a = accs + ((to % 3) * 4 + fs) * DEC_WB;
+        float* eo = est + ((((size_t)b * n_src + fs) * n_frames + to) * n_freq + o0) * 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int lo = fj + 64 * h;                          // output bin o0 + lo lives in accumulator bin 2 + lo
+          const float2 v = a[2 + lo];
+          if (lo < wout && fs < n_src) *reinterpret_cast<float2*>(eo + 2 * lo) = v;
+          a[2 + lo] = fbias;
+        }
+        if (fj < 4) a[fj < 2 ? fj : 128 + fj] = fbias;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
 // Full-track stitch: track[src][s0 + m] += w(m) * seg[src][b][m] (oracle/stitch.py; new
 // behaviour).  Periodic-Hann cross-fade, flat outer edges.
 // --------------------------------------------------------------------------------------

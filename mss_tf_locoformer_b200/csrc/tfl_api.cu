@@ -21,7 +21,7 @@
 namespace tfl {
 
 static thread_local char g_err[1024] = "";
-static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {2}, {0}, {0}};   // tfl_debug_set_option
+static std::atomic<int> g_options[TFL_OPT_COUNT] = {{2}, {2}, {0}, {2}, {0}, {2}, {2}, {0}};   // tfl_debug_set_option
 int tfl_option(int key) { return g_options[key].load(std::memory_order_relaxed); }
 std::atomic<unsigned long long> g_launches{0};
 
@@ -699,6 +699,43 @@ static int dec_conv_any(const tfl_plan* pl, const void* packed, const float* x, 
   if (precision != TFL_PRECISION_BF16 || C % 16 != 0 || pl->cfg.n_src * 2 > 8) return tfl_dec_conv(pl, packed, x, B, Tf, F, est, stream);
   NvtxRange nvtx_range("tfl::dec_conv[tf32]");
   if (check_common(pl, packed, B, Tf, F, precision)) return -1;
+  if (C % 32 == 0 && C <= 128 && tfl_option(TFL_OPT_DEC_KERNEL) != 1) {
+    // scatter form: every x row read once; strips of equal width, frame runs sized so that the items fill whole waves
+    const int NS = (F + DEC_WOUT - 1) / DEC_WOUT, WOUT = (F + NS - 1) / NS;
+    const int slots = 2 * pl->sm_count;
+    int NR = 1;
+    for (int w = 1; w <= 16; ++w) {
+      long long nr = (long long)slots * w / ((long long)B * NS);
+      if (nr < 1) continue;
+      if (nr > (Tf + 3) / 4) nr = (Tf + 3) / 4;
+      NR = (int)nr;
+      if ((Tf + NR - 1) / NR <= 80) break;
+    }
+    const int R = (Tf + NR - 1) / NR;
+    NR = (Tf + R - 1) / R;
+    const long long items = (long long)B * NS * NR;
+    const int grid = (int)(items < slots ? items : slots);
+    const size_t smem = ((size_t)72 * (C + 16) + (size_t)3 * 4 * DEC_WB * 2) * sizeof(float);
+    const char* base = (const char*)packed;
+    const float* wd = (const float*)(base + pl->lay.dec_w);
+    const float* bd = (const float*)(base + pl->lay.dec_b);
+    const int n_out = pl->cfg.n_src * 2;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TFL_DEC_SCATTER(NCH)                                                                                    \
+    {                                                                                                           \
+      TFL_CUDA(opt_in_smem(dec_conv_scatter_kernel<NCH>, smem));                                                \
+      dec_conv_scatter_kernel<NCH><<<grid, 256, smem, st>>>(x, B, Tf, F, n_out, wd, bd, est, NS, WOUT, NR, R);  \
+    }
+    switch (C / 32) {
+      case 1: TFL_DEC_SCATTER(1) break;
+      case 2: TFL_DEC_SCATTER(2) break;
+      case 3: TFL_DEC_SCATTER(3) break;
+      default: TFL_DEC_SCATTER(4) break;
+    }
+#undef TFL_DEC_SCATTER
+    TFL_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)9 * C * 8 * sizeof(float);
   TFL_CUDA(opt_in_smem(dec_conv_mma_kernel, smem));
   const char* base = (const char*)packed;
@@ -714,6 +751,13 @@ static int dec_conv_any(const tfl_plan* pl, const void* packed, const float* x, 
 }
 }  // namespace tfl
 extern "C" {
+
+int tfl_dec_conv_mode(const tfl_plan* pl, const void* packed, const float* x, int B, int Tf, int F, float* est,
+                      int precision, tfl_stream_t stream) {
+  TFL_CHECK(pl && packed && x && est, "null argument");
+  TFL_CHECK(pl->cfg.enc_in_ch == 2, "plan has no conv decoder");
+  return dec_conv_any(pl, packed, x, B, Tf, F, est, precision, stream);
+}
 
 int tfl_dec_conv(const tfl_plan* pl, const void* packed, const float* x, int B, int Tf, int F, float* est,
                  tfl_stream_t stream) {

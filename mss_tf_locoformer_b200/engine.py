@@ -194,13 +194,13 @@ class Engine:
                                             F, x.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
         return x
 
-    def dec_conv(self, x: torch.Tensor) -> torch.Tensor:
+    def dec_conv(self, x: torch.Tensor, precision: int = 0) -> torch.Tensor:
         _require_cuda(x, "x")
         B, Tf, F, _ = x.shape
         est = torch.empty((B, self.cfg["n_src"], Tf, F, 2), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            check(self.lib.tfl_dec_conv(self.plan, self.packed.data_ptr(), x.contiguous().data_ptr(), B, Tf, F,
-                                        est.data_ptr(), _stream()))
+            check(self.lib.tfl_dec_conv_mode(self.plan, self.packed.data_ptr(), x.contiguous().data_ptr(), B, Tf, F,
+                                             est.data_ptr(), precision, _stream()))
         return est
 
     def rms_group_norm(self, layer: int, axis: int, which: int, x: torch.Tensor) -> torch.Tensor:

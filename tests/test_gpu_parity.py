@@ -382,3 +382,45 @@ def test_espnet_adapter_forward(pkg):
     for s, o in enumerate(outs):
         _check(o, arr["spec_out"][:, s], maxabs=2e-4, what=f"espnet/spk{s}")
         assert torch.equal(o, outs4[s])
+
+
+@pytest.mark.parametrize("emb,n_src,batch,n_frames,n_freq", [
+    (128, 4, 2, 7, 1025),     # BASELINE width, nine strips (eight full + 17 bins)
+    (128, 4, 1, 1, 129),      # a single frame: every output flushed by the last-frame clause
+    (128, 4, 3, 2, 126),      # exactly one full strip
+    (128, 4, 40, 3, 127),     # more (sample, strip, run) items than resident blocks: accumulators reused across items
+    (96, 4, 2, 9, 513),       # Variant Y width (three 32-channel chunks)
+    (64, 2, 2, 5, 65),        # two sources (outputs 4..7 unused), F < 126
+    (32, 4, 1, 300, 33),      # long frame axis split into runs with halo frames
+])
+def test_decoder_bf16_mode_kernels(pkg, emb, n_src, batch, n_frames, n_freq):
+    """K6 in bf16 mode (tf32 mma.sync): the scatter-form kernel (default) and the 9-tap gather kernel against the
+    oracle's ConvTranspose2d restatement (models/mss_tflocoformer.py:182) in float64.  tf32 operands: 2^-11 relative
+    per product, so the gate is 2e-3 of the output scale; the two kernels share operands and differ only in summation
+    order.  The scatter kernel's summation order does not depend on the batch index or on the strip / run split:
+    a sample computed alone is bit-identical to the same sample inside a batch."""
+    from mss_tf_locoformer_b200 import _lib
+    lib = _lib.load()
+    cfg = dict(VARIANT_D, emb_dim=emb, attention_dim=emb, n_sources=n_src, ffn_hidden_dim=[64, 64])
+    model = _random_model(pkg, cfg).cuda()
+    eng = model._ready()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, n_frames, n_freq, emb, generator=g)
+    want = oracle.decoder(x.double(), sd["deconv.weight"].double(), sd["deconv.bias"].double())
+    want = want.reshape(batch, n_frames, n_freq, n_src, 2).permute(0, 3, 1, 2, 4)
+    scale = float(want.abs().max())
+    got = {}
+    try:
+        for opt in (2, 1):
+            assert lib.tfl_debug_set_option(6, opt) == 0
+            got[opt] = eng.dec_conv(x.cuda(), 1).cpu()
+            err = float((got[opt].double() - want).abs().max())
+            assert err <= 2e-3 * scale, (opt, err, scale)
+        assert float((got[1] - got[2]).abs().max()) <= 1e-4 * scale
+        lib.tfl_debug_set_option(6, 2)
+        b = batch - 1
+        alone = eng.dec_conv(x[b:b + 1].cuda(), 1).cpu()
+        assert torch.equal(alone[0], got[2][b])
+    finally:
+        lib.tfl_debug_set_option(6, 2)
