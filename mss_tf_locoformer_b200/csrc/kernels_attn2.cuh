@@ -45,6 +45,9 @@ struct Attn2Params {
 #ifndef ATT2_PREFETCH
 #define ATT2_PREFETCH 0   // 1: read the scores of half k + 1 back before the exp2 pass of half k (measured SLOWER, r02)
 #endif
+#ifndef ATT2_QUARTER
+#define ATT2_QUARTER 0    // 1: 16-key quarters, the read-back of the next quarter in flight during the exp2 pass of this one (measured SLOWER, r02: 4.66 vs 4.47 ms per frequency-axis sub-block)
+#endif
 constexpr int ATT2_G = 4;
 constexpr int ATT2_MMA_WARPS = ATT2_G / 2;                           // one MMA warp per pair of groups
 constexpr int ATT2_THREADS = 32 * (4 * ATT2_G + 4);   // softmax warps; one warpgroup of MMA warps, loader and an idle warp
@@ -169,6 +172,59 @@ __device__ __forceinline__ void attn2_half(uint32_t (&s)[32], uint32_t tcol, uin
     }
   }
   tc_wait_st();
+}
+
+// ---- 16-key quarters (ATT2_QUARTER) ----
+// TMEM read-back (64 B/clk per SM) and the exp2 unit each need ~1 024 clk per 32-key half-step of the 16 softmax warps,
+// and a warp used them strictly one after the other (tcgen05.ld of 32 columns -> wait -> 32 exp2).  Here a half is
+// read back as two 16-column quarters into the SAME 32 registers: while the exp2 pass of one quarter runs, the
+// read-back of the next one (the second quarter of this half, or the first quarter of the next half) is in flight.
+// No second score set (the 32 + 32 register variant, ATT2_PREFETCH, spilled) and no extra barrier in front of the
+// exp2 burst.  The lazy reference makes this possible: a quarter's probabilities never wait for the maximum of the
+// other quarter -- only the rare raise (a score more than 2^ATT2_TH above the reference) has to redo the first
+// quarter's probabilities when the second quarter triggers it.
+__device__ __forceinline__ float attn2_max16(const uint32_t (&s)[16]) {
+  float m0 = max3f(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+  float m1 = max3f(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
+  float m2 = max3f(__uint_as_float(s[6]), __uint_as_float(s[7]), __uint_as_float(s[8]));
+  float m3 = max3f(__uint_as_float(s[9]), __uint_as_float(s[10]), __uint_as_float(s[11]));
+  m0 = max3f(m0, __uint_as_float(s[12]), __uint_as_float(s[13]));
+  m1 = max3f(m1, __uint_as_float(s[14]), __uint_as_float(s[15]));
+  return max3f(max3f(m0, m1, m2), m3, m3);
+}
+template <bool SUM>
+__device__ __forceinline__ void attn2_exp16(const uint32_t (&s)[16], float m_ref, uint32_t (&pk)[8], float& l0, float& l1) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float p0 = fast_exp2(__uint_as_float(s[2 * i]) - m_ref);
+    const float p1 = fast_exp2(__uint_as_float(s[2 * i + 1]) - m_ref);
+    if (SUM) { l0 += p0; l1 += p1; }
+    pk[i] = tc::pack_bf16(p0, p1);
+  }
+}
+// rare: raise the reference to m_new and rescale what has been accumulated (O in TMEM when have_o, the row sums)
+__device__ __forceinline__ void attn2_raise(uint32_t tcol, uint32_t bgrp, int bb, uint32_t ph, bool have_o, int HDP,
+                                            float m_new, float& m_ref, float& l0, float& l1) {
+  using namespace tc;
+  constexpr uint32_t PV_DONE = 48;
+  const float alpha = fast_exp2(m_ref - m_new);
+  if (have_o) {
+    // every P.V issued so far must have landed; MMAs complete in issue order: wait for the one of the previous half
+    const int pb = bb == 0 ? 2 : bb - 1;
+    mbar_wait(bgrp + PV_DONE + 8 * pb, bb == 0 ? ph ^ 1 : ph);
+    tc_fence_after();
+    for (int c0 = 0; c0 < HDP; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tcol + 96 + c0, r);
+      tc_wait_ld();                                              // (also drains a score read-back in flight: harmless)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+      tmem_st16(tcol + 96 + c0, r);
+    }
+    tc_wait_st();
+  }
+  l0 *= alpha; l1 *= alpha;
+  m_ref = m_new;
 }
 
 template <int KS>   // K steps of S = Q K^T (head_dim padded to 16 * KS)
@@ -453,6 +509,59 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_tc2_kernel(Attn2Params p
         if (k < NH) ATT2_STEP(sB, sA)
       }
 #undef ATT2_STEP
+#elif ATT2_QUARTER
+      uint32_t sA[16], sB[16];
+      mbar_wait(bgrp + S_FULL + 8 * bb, ph);
+      tc_fence_after();
+      tmem_ld16(tcol + bb * 32, sA);                               // first quarter of the item's first half
+      for (int k = 0; k < NH; ++k, ++kk) {
+        const int nk = k < n_full ? 32 : n_last;                   // keys in this half
+        tc_wait_ld();                                              // sA: scores 0..15 of half k
+        tmem_ld16(tcol + bb * 32 + 16, sB);                        // scores 16..31 in flight during the first exp2 pass
+        if (nk < 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (i >= nk) sA[i] = 0xff800000u;
+        }
+        const float mxa = attn2_max16(sA);
+        if (k == 0) {
+          m_ref = mxa;
+        } else if (__any_sync(0xffffffffu, mxa > m_ref + ATT2_TH)) {
+          attn2_raise(tcol, bgrp, bb, ph, true, HDP, mxa > m_ref + ATT2_TH ? mxa : m_ref, m_ref, l0, l1);
+        }
+        if (kk >= 3) mbar_wait(bgrp + PV_DONE + 8 * bb, ph ^ 1);   // phase bookkeeping only (see attn2_half)
+        uint32_t pk[8];
+        attn2_exp16<true>(sA, m_ref, pk, l0, l1);
+        tmem_st8(tcol + bb * 32, pk);
+        tc_wait_ld();                                              // sB
+        if (nk < 32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (16 + i >= nk) sB[i] = 0xff800000u;
+        }
+        const float mxb = attn2_max16(sB);
+        if (__any_sync(0xffffffffu, mxb > m_ref + ATT2_TH)) {
+          // the second quarter raises the reference: the first quarter's probabilities were written against the old one
+          attn2_raise(tcol, bgrp, bb, ph, k > 0, HDP, mxb > m_ref + ATT2_TH ? mxb : m_ref, m_ref, l0, l1);
+          tc_wait_st();
+          attn2_exp16<false>(sA, m_ref, pk, l0, l1);
+          tmem_st8(tcol + bb * 32, pk);
+        }
+        const int nb = bb == 2 ? 0 : bb + 1;
+        const uint32_t nph = bb == 2 ? ph ^ 1 : ph;
+        if (k + 1 < NH) {                                          // sA is dead: first quarter of the next half
+          mbar_wait(bgrp + S_FULL + 8 * nb, nph);
+          tc_fence_after();
+          tmem_ld16(tcol + nb * 32, sA);
+        }
+        if (nk > 16) {
+          attn2_exp16<true>(sB, m_ref, pk, l0, l1);
+          tmem_st8(tcol + bb * 32 + 8, pk);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bgrp + P_FULL + 8 * bb);
+        lb = bb; lph = ph;
+        bb = nb; ph = nph;
+      }
 #else
       for (int k = 0; k < NH; ++k, ++kk) {
         mbar_wait(bgrp + S_FULL + 8 * bb, ph);

@@ -1,4 +1,6 @@
 """GPU tests of the tcgen05 / TMEM path (TFL_PRECISION_BF16)."""
+import math
+
 import pytest
 import torch
 
@@ -211,3 +213,49 @@ def test_ffn_tc_kernel_variants_agree(pkg):
         branch = (a - xin).float()
         assert float((a - b).abs().max()) <= 2e-2 * float(branch.abs().max())   # the 2-CTA kernel's order of accumulation differs
         assert oracle.si_sdr_db((b - xin).cpu(), branch.cpu()) > 50.0
+
+
+def test_attention_tc_reference_raise(pkg):
+    """The lazy softmax reference of attn_tc2_kernel: with q / k weights scaled by 6 the scores spread over ~18 log2
+    units, so that in most rows a later key exceeds the reference taken from the first 16 keys by more than
+    2^ATT2_TH -- the rare path that raises the reference, rescales O and the row sums and (when the second 16-key
+    quarter of a half triggers it) redoes the first quarter's probabilities.  Checked against the oracle (sharp
+    softmax amplifies the bf16 rounding of q and k: 20 dB gate) and against attn_tc_kernel, which keeps a true running
+    maximum and reads the same bf16 images (40 dB)."""
+    from mss_tf_locoformer_b200 import _lib
+    from oracle.locoformer_oracle import rope_rotate
+    lib = _lib.load()
+    cfg = dict(VARIANT_D)
+    model = _random_model(pkg, cfg)
+    with torch.no_grad():
+        for path in ("freq_path", "frame_path"):
+            getattr(model.blocks[0], path).attn.qkv.weight[:2 * cfg["attention_dim"]] *= 6.0
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    xin = torch.randn(1, 130, 300, cfg["emb_dim"], generator=g)
+    model = model.cuda().eval()
+    eng = model._ready()
+    hd = cfg["attention_dim"] // cfg["n_heads"]
+    for axis, path in ((0, "freq_path"), (1, "frame_path")):
+        p = f"blocks.0.{path}"
+        xa = xin if axis == 0 else xin.transpose(1, 2).contiguous()
+        b, s1, s2, c = xa.shape
+        xn = oracle.rms_group_norm(xa, sd[f"{p}.attn_norm.gamma"], cfg["num_groups"], cfg["eps"]).reshape(b * s1, s2, c)
+        # the case must exercise the path: rows whose later keys exceed the first quarter's maximum by > 16 log2 units
+        qkv = (xn[:8] @ sd[f"{p}.attn.qkv.weight"].t()).reshape(8, s2, 3, cfg["n_heads"], hd).permute(2, 0, 3, 1, 4)
+        q, k = rope_rotate(qkv[0], sd[f"{p}.attn.rope.freqs"]), rope_rotate(qkv[1], sd[f"{p}.attn.rope.freqs"])
+        s = (q @ k.transpose(-1, -2)) / math.sqrt(hd) * math.log2(math.e)
+        jump = s[..., 16:].max(-1).values - s[..., :16].max(-1).values
+        assert float((jump > 16.0).float().mean()) > 0.3
+        y = oracle.attention(xn, sd[f"{p}.attn.qkv.weight"], sd[f"{p}.attn.aggregate_heads.0.weight"], cfg["n_heads"],
+                             sd.get(f"{p}.attn.rope.freqs")).reshape(xa.shape)
+        branch = y if axis == 0 else y.transpose(1, 2)
+        got = {}
+        try:
+            for opt in (2, 1):
+                assert lib.tfl_debug_set_option(0, opt) == 0
+                got[opt] = eng.attn_(0, axis, xin.cuda().clone(), 1).cpu() - xin
+        finally:
+            lib.tfl_debug_set_option(0, 2)
+        assert oracle.si_sdr_db(got[2], branch) > 20.0, (axis, oracle.si_sdr_db(got[2], branch))
+        assert oracle.si_sdr_db(got[2], got[1]) > 40.0, (axis, oracle.si_sdr_db(got[2], got[1]))
