@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ aud
 // --------------------------------------------------------------------------------------
 // K7 istft_ola: one CTA per (run of ISTFT_RUN hop blocks, source, batch).  For each frame overlapping the
 // run: Hermitian-extend, inverse FFT in smem, window, accumulate; then divide by the sum of squared windows
-// and store (:56-75).  Output audio[src][b][n].  A run of 8 blocks needs 8 + n_fft/hop - 1 inverse FFTs
+// and store (:56-75).  Output audio[src][b][n].  The inverse real FFT is ONE complex FFT of n_fft/2 points (even /
+// odd samples as real / imaginary parts) in radix-4 passes: 5 passes of 256 four-point butterflies at n_fft 2048
+// where the full-size radix-2 version ran 11 passes of 1024 butterflies.  A run of 8 blocks needs 8 + n_fft/hop - 1 inverse FFTs
 // (9 at hop = n_fft/2) where one CTA per block needed n_fft/hop each (16): the FFT passes were what the
 // kernel spent its time on (ncu r02: shared-memory pipe 99 % busy).  Frames are added in increasing
 // order: deterministic.  Twiddles are staged in shared memory once per CTA.
@@ -86,6 +88,47 @@ __device__ __forceinline__ void fft_smem_tw(float2* buf, const float2* tws, int 
       const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
       buf[a] = make_float2(u.x + tr, u.y + ti);
       buf[b] = make_float2(u.x - tr, u.y - ti);
+    }
+    __syncthreads();
+  }
+}
+
+// Radix-4 decimation-in-time passes over bit-reversed input (two radix-2 stages per pass in registers: half the
+// shared-memory traffic and barriers, 3 instead of 4 twiddle products per 4 points; one leading radix-2 pass when
+// log_n is odd).  tws[m] = exp(-2 pi i m / (n << tw_shift)), first half of the circle.
+template <bool INVERSE>
+__device__ __forceinline__ void fft_smem_r4(float2* buf, const float2* tws, int n, int log_n, int tw_shift) {
+  int s = 1;
+  if (log_n & 1) {
+    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+      const float2 u = buf[2 * i], v = buf[2 * i + 1];
+      buf[2 * i] = make_float2(u.x + v.x, u.y + v.y);
+      buf[2 * i + 1] = make_float2(u.x - v.x, u.y - v.y);
+    }
+    __syncthreads();
+    s = 2;
+  }
+  for (; s < log_n; s += 2) {                              // stages s and s + 1
+    const int h = 1 << (s - 1);
+    for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) {
+      const int j = i & (h - 1);
+      const int i0 = ((i >> (s - 1)) << (s + 1)) + j;
+      float2 w = tws[(j << (log_n - s)) << tw_shift];      // exp(-2 pi i j / 2^s)
+      float2 v = tws[(j << (log_n - s - 1)) << tw_shift];  // exp(-2 pi i j / 2^(s+1))
+      if (INVERSE) { w.y = -w.y; v.y = -v.y; }
+      const float2 x0 = buf[i0], x1 = buf[i0 + h], x2 = buf[i0 + 2 * h], x3 = buf[i0 + 3 * h];
+      const float2 t1 = make_float2(x1.x * w.x - x1.y * w.y, x1.x * w.y + x1.y * w.x);
+      const float2 t3 = make_float2(x3.x * w.x - x3.y * w.y, x3.x * w.y + x3.y * w.x);
+      const float2 u0 = make_float2(x0.x + t1.x, x0.y + t1.y), u1 = make_float2(x0.x - t1.x, x0.y - t1.y);
+      const float2 u2 = make_float2(x2.x + t3.x, x2.y + t3.y), u3 = make_float2(x2.x - t3.x, x2.y - t3.y);
+      const float2 pp = make_float2(u2.x * v.x - u2.y * v.y, u2.x * v.y + u2.y * v.x);
+      const float2 qq = make_float2(u3.x * v.x - u3.y * v.y, u3.x * v.y + u3.y * v.x);
+      // second-stage twiddle of the odd pair: v * exp(-+ i pi / 2), i.e. qq * (-i) forward, qq * (+i) inverse
+      const float2 q = INVERSE ? make_float2(-qq.y, qq.x) : make_float2(qq.y, -qq.x);
+      buf[i0] = make_float2(u0.x + pp.x, u0.y + pp.y);
+      buf[i0 + 2 * h] = make_float2(u0.x - pp.x, u0.y - pp.y);
+      buf[i0 + h] = make_float2(u1.x + q.x, u1.y + q.y);
+      buf[i0 + 3 * h] = make_float2(u1.x - q.x, u1.y - q.y);
     }
     __syncthreads();
   }
@@ -114,24 +157,25 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict_
   for (int t = t_min; t <= t_max; ++t) {
     const float2* x = reinterpret_cast<const float2*>(est) + (((size_t)b * n_src + src) * n_frames + t) * n_freq;
     __syncthreads();
-    for (int k = threadIdx.x; k < n_freq; k += blockDim.x) {
-      float2 v = __ldg(&x[k]);
-      if (k == 0 || k == pad) {
-        v.y = 0.f;  // irfft ignores the imaginary part of DC and Nyquist
-        fbuf[bitrev(k, log_n)] = v;
-      } else {
-        fbuf[bitrev(k, log_n)] = v;
-        fbuf[bitrev(n_fft - k, log_n)] = make_float2(v.x, -v.y);
-      }
+    // Real output: one complex inverse FFT of HALF the size.  With E[k] = X[k] + conj(X[N/2 - k]) and
+    // O[k] = (X[k] - conj(X[N/2 - k])) exp(+2 pi i k / N), z = IDFT_{N/2}(E + i O) holds z[n] = N (x[2n] + i x[2n+1]):
+    // the frame's samples are the float view of fbuf.
+    for (int k = threadIdx.x; k < pad; k += blockDim.x) {
+      float2 a = __ldg(&x[k]), c = __ldg(&x[pad - k]);
+      if (k == 0) { a.y = 0.f; c.y = 0.f; }                // irfft ignores the imaginary part of DC and Nyquist
+      const float2 e = make_float2(a.x + c.x, a.y - c.y), d = make_float2(a.x - c.x, a.y + c.y);
+      const float2 w = tws[k];                             // exp(-2 pi i k / N); O = d * conj(w)
+      const float2 o = make_float2(d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y);
+      fbuf[bitrev(k, log_n - 1)] = make_float2(e.x - o.y, e.y + o.x);
     }
     __syncthreads();
-    fft_smem_tw<true>(fbuf, tws, n_fft, log_n);
+    fft_smem_r4<true>(fbuf, tws, pad, log_n - 1, 1);
     // samples of this frame that fall into the run: padded coordinate t * hop + off, off in [0, n_fft)
     const int lo = max(0, t * hop - q_lo), hi = min(span, t * hop + n_fft - q_lo);
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
       const int off = q_lo + i - t * hop;
       const float w = __ldg(&win[off]);
-      acc[i] += fbuf[off].x * inv_n * w;
+      acc[i] += reinterpret_cast<const float*>(fbuf)[off] * inv_n * w;
       env[i] += w * w;
     }
   }
