@@ -6,7 +6,10 @@ Every arithmetic step is a kernel reached through include/tfl.h (``tfl_train_for
 ``tfl_adamw_step``); torch holds the buffers and, when ``torch.distributed`` is initialised, all-reduces the ONE flat
 gradient buffer (NCCL over NVLink; the reference itself has no multi-GPU training).
 
-fp32 on CUDA cores (the parity mode of the forward path); dropout is not applied (parity is defined for p = 0).
+Arithmetic (``tfl_debug_set_option(TFL_OPT_TRAIN_MODE, m)``): 0 = exact fp32 on CUDA cores (the gradient-parity mode),
+1 = tf32 ``mma.sync`` GEMMs, 2 (default) = forward of the sub-blocks on the bf16 tcgen05 inference kernels and bf16 / tf32
+``mma.sync`` backward.  Dropout is not applied (parity is defined for p = 0): a model built with
+``dropout > 0`` is refused.
 """
 import ctypes as C
 from typing import Dict, Optional, Union
