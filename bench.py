@@ -353,6 +353,15 @@ def time_reference_gpu_train(cfg, sd, dev, mix, tgt, steps, loss_w):
         return "failed: " + str(e).splitlines()[0][:160]
 
 
+def train_dtype(cfg):
+    """Operand type of the training step's GEMMs in the default TFL_OPT_TRAIN_MODE 2 (accumulation is fp32 everywhere):
+    bf16 where the tcgen05 attention path takes the shape (csrc/kernels_attn.cuh attn_tc_supported), else tf32."""
+    hd = cfg["attention_dim"] // cfg["n_heads"]
+    npart = cfg["n_heads"] * ((hd + 15) // 16 * 16)
+    ok = hd % 2 == 0 and hd <= 32 and npart % 32 == 0 and npart <= 128 and cfg["emb_dim"] % 16 == 0
+    return "bf16" if ok else "tf32"
+
+
 def run_train(args, dev, rank, world):
     """BASELINE config 5: one data-parallel training step per `step` (forward, MSSLoss, backward, NCCL gradient average,
     clip, AdamW) through mss_tf_locoformer_b200.training.Trainer; every rank trains on its own sample(s)."""
@@ -421,7 +430,7 @@ def run_train(args, dev, rank, world):
     print(json.dumps({
         "metric": "trained audio-sec/sec (forward + loss + backward + gradient all-reduce + clip + AdamW)",
         "value": world * secs / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": train_dtype(cfg), "data": "synthetic",
         "config": {"workload": what, "batch_per_gpu": B, "seconds_per_sample": n_samples / SR, "parallelism": f"dp{world}",
                    "loss": "MSSLoss combined (si_sdr 1.0, l1 0.1, spectral 0.15)", "optimizer": "AdamW lr 3e-4 wd 0.01, clip 5.0",
                    "params": int(sum(p.numel() for p in model.parameters() if p.requires_grad)),
