@@ -95,3 +95,38 @@ def test_metric_closed_forms_match_reference_formulas():
     want = 10 * np.log10((np.dot(t, t) + eps) / (np.dot(e - t, e - t) + eps))
     got = 10 * math.log10((s[3] + eps) / (s[2] - 2 * s[4] + s[3] + eps))
     assert abs(got - want) < 1e-8
+
+
+def test_bench_reference_arm_line(monkeypatch, capsys):
+    """bench.py --impl reference: rank 0 alone prints ONE JSON line whose metric / unit / config are the b200 arm's (the
+    bounded sample is named in cpu_baseline.sample), with the reference-arm keys of the measurement contract; other
+    ranks print nothing.  The CPU forward itself is stubbed here (it takes a minute per 6-s segment)."""
+    import argparse
+    import json
+    import bench
+
+    class Stub:
+        def __call__(self, mix):
+            return {"vocals": mix}
+
+    monkeypatch.setattr(bench, "reference_model", lambda cfg, sd, device="cpu": (Stub(), "reference"))
+    monkeypatch.setattr(bench, "make_state_dict", lambda cfg, seed=0: torch.nn.Linear(1, 1))
+    args = argparse.Namespace(variant="D", steps=2, warmup=1, gpus=2, batch=8)
+    bench.run_reference(args, rank=1)
+    assert capsys.readouterr().out == ""
+    bench.run_reference(args, rank=0)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 2 and line["steps"] == 2 and line["warmup"] == 1
+    assert line["config"] == bench.workload_config("D", 8)
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["value"] == line["value"]
+    assert "6.00-s mono segment" in line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_train_dtype_names_the_operand_type():
+    import bench
+    assert bench.train_dtype(bench.TRAIN_CFGS["D"][0]) == "bf16"          # tcgen05 forward + bf16 mma.sync backward
+    assert bench.train_dtype(bench.TRAIN_CFGS["xlarge"][0]) == "tf32"     # 16 heads x 16 at emb 256: tf32 mma.sync
