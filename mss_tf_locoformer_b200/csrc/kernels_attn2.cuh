@@ -45,6 +45,9 @@ struct Attn2Params {
 #ifndef ATT2_PREFETCH
 #define ATT2_PREFETCH 0   // 1: read the scores of half k + 1 back before the exp2 pass of half k (measured SLOWER, r02)
 #endif
+#ifndef ATT2_POLY_MASK
+#define ATT2_POLY_MASK 0x00  // bit i: pair i of every 8 pairs of a half takes its two exponentials from the FMA pipe (exp2_poly) instead of MUFU.EX2
+#endif
 #ifndef ATT2_QUARTER
 #define ATT2_QUARTER 0    // 1: 16-key quarters, the read-back of the next quarter in flight during the exp2 pass of this one (measured SLOWER, r02: 4.66 vs 4.47 ms per frequency-axis sub-block)
 #endif
@@ -109,6 +112,20 @@ inline uint32_t attn2_smem(int HDP, int HG, int* NS_out) {
   return fixed + (uint32_t)NS * stage;
 }
 
+// 2^x on the FMA pipe for x <= ATT2_TH (Cody-Waite: n = round(x) through the 1.5 * 2^23 magic add, f = x - n in
+// [-0.5, 0.5], degree-3 minimax polynomial of 2^f with 7.5e-5 relative error -- 26 times below the bf16 rounding of the
+// probability -- and n added straight into the exponent field).  The clamp keeps the exponent field positive: masked
+// scores (-inf) come out as 2^-125 instead of 0, against key / value rows that are exact zeros.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float xr = x + 12582912.f;
+  const float f = x - (xr - 12582912.f);
+  float p = fmaf(0.0551716648f, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xr) << 23));
+}
+
 // One 32-key half for one query row: scores s[] (already read from TMEM buffer bb) -> max -> [rare: raise m_ref, rescale
 // O] -> exp2 -> bf16 P written over the first 16 columns of the same buffer.  FULL: all 32 columns are keys; otherwise
 // nkh are.  The read-back itself is issued by the caller one half AHEAD (ATT2_PREFETCH): TMEM reads run at 64 B/clk per
@@ -163,8 +180,10 @@ __device__ __forceinline__ void attn2_half(uint32_t (&s)[32], uint32_t tcol, uin
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float p0 = fast_exp2(__uint_as_float(s[16 * c + 2 * i]) - m_ref);
-        const float p1 = fast_exp2(__uint_as_float(s[16 * c + 2 * i + 1]) - m_ref);
+        const float x0 = __uint_as_float(s[16 * c + 2 * i]) - m_ref, x1 = __uint_as_float(s[16 * c + 2 * i + 1]) - m_ref;
+        const bool poly = ((ATT2_POLY_MASK >> i) & 1) != 0;
+        const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
+        const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
         l0 += p0; l1 += p1;
         pk[i] = pack_bf16(p0, p1);
       }
